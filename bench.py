@@ -1,0 +1,240 @@
+"""Headline benchmark (BASELINE.json): training tokens/s of Llama-2-7B, seq 4096, bf16, on N B200s
+of one node — DDP + ZeRO-1 for N > 1 (chapter 02's configuration), one process per GPU.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        --master-port 29533 bench.py --gpus 8 --steps 5 --warmup 3
+    python bench.py --impl reference ...      # the UNMODIFIED reference script from baseline/_ref
+
+Protocol: W untimed warm-up steps, then K steps bracketed by barrier + cuda.synchronize, timed
+with CUDA events on the device, max over ranks.  Two timed regions:
+  * ``value``  — device-timed step loop with the batch already resident on the GPU;
+  * ``e2e``    — the same K steps through the public API (``TrainEngine.step``) with, every step, the
+                 host->device copy of that step's tokens from pinned memory and a device->host read
+                 of the loss.
+Synthetic tokens, random-init weights (no network on the box).  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "tokens/sec (device-timed, max over ranks) Llama-2-7B seq 4096 bf16 training"
+PARALLELISM_NAMES = {"ddp": "dp", "fsdp": "fsdp", "tp": "tp", "2d": "fsdp_x_tp", "single": "single"}
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons of one GPU during the timed region (NVML)."""
+
+    def __init__(self, index: int, period_s: float = 0.2):
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+
+    def _loop(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+                "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+            }
+            while not self._stop.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for k, bit in names.items():
+                        if r & bit:
+                            self.reasons.add(k)
+                except Exception:
+                    pass
+                time.sleep(self.period)
+        except Exception as e:  # NVML missing: fall back to one nvidia-smi query
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._loop, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=2)
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
+    ap.add_argument("--model", default="meta-llama/Llama-2-7b-hf")
+    ap.add_argument("--seq-len", type=int, default=4096)
+    ap.add_argument("--batch", type=int, default=1, help="per-GPU micro batch (weak scaling)")
+    ap.add_argument("--parallelism", default="ddp", choices=("ddp", "fsdp", "tp", "2d"))
+    ap.add_argument("--tensor-parallel", type=int, default=None)
+    ap.add_argument("--layers", type=int, default=None,
+                    help="DEBUG ONLY: truncate the model; such a number is not a valid benchmark value")
+    return ap.parse_args()
+
+
+def _dist_max(x: float, device) -> float:
+    import torch
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return x
+
+
+def _barrier_sync(device):
+    import torch
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+
+
+def run_b200(args):
+    import torch
+
+    from distributed_training_guide_b200 import _ext
+    from distributed_training_guide_b200.engine import TrainEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun for N>1"
+    par = args.parallelism if world > 1 else "single"
+    eng = TrainEngine.create(args.model, parallelism=par, batch_size=args.batch, seq_length=args.seq_len,
+                             tensor_parallel=args.tensor_parallel, num_layers=args.layers)
+    dev = eng.device
+    rank = eng.env.rank
+    host_batches = [eng.synthetic_batch(seed=i) for i in range(4)]
+    dev_batches = [{k: v.to(dev) for k, v in b.items()} for b in host_batches]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host_batches[0].values())
+
+    for i in range(args.warmup):
+        eng.step(dev_batches[i % 4])
+    # ---- region 1: device-timed steps, batch resident on the GPU --------------------------------
+    _barrier_sync(dev)
+    l0 = _ext.launch_count()
+    with ClockSampler(dev.index or 0) as clocks:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(args.steps):
+            loss = eng.step(dev_batches[i % 4])
+        e.record()
+        _barrier_sync(dev)
+    launches = _ext.launch_count() - l0
+    ms_dev = _dist_max(s.elapsed_time(e), dev) / args.steps
+    # ---- region 2: end to end through the public API: pinned H2D every step + loss D2H every step ---
+    eng.step(host_batches[0])
+    _barrier_sync(dev)
+    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    s2.record()
+    last = 0.0
+    for i in range(args.steps):
+        loss = eng.step(host_batches[i % 4])
+        last = loss.item()  # 4-byte device->host read of the step's result
+    e2.record()
+    _barrier_sync(dev)
+    wall_ms = 1000 * (time.perf_counter() - t0)
+    ms_e2e = _dist_max(max(s2.elapsed_time(e2), wall_ms), dev) / args.steps
+
+    tokens = eng.tokens_per_step
+    value = 1000.0 * tokens / ms_dev
+    dp = eng.strategy.dp_size
+    tp = getattr(eng.strategy, "tp_size", 1)
+    pname = PARALLELISM_NAMES[par]
+    par_str = "single" if world == 1 else (f"dp{dp}" if par in ("ddp", "fsdp") and tp == 1 else f"dp{dp}xtp{tp}")
+    out = {
+        "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic tokens, random-init weights",
+        "impl": "b200",
+        "config": {"model": args.model + (f"[layers={args.layers}]" if args.layers else ""),
+                   "global_batch": dp * args.batch, "seq_len": args.seq_len,
+                   "parallelism": par_str + (f" ({pname}+zero1)" if par == "ddp" and world > 1 else f" ({pname})"),
+                   "optimizer": "AdamW bf16 states (as reference)",
+                   "l2": "per-step working set (>50 GB of weights/grads/activations) far exceeds the 126 MB L2"},
+        "clocks": clocks.summary(),
+        "e2e": {"value": 1000.0 * tokens / ms_e2e, "unit": "tokens/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "final_loss": last,
+        "peak_alloc_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
+    }
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    eng.close()
+
+
+def run_reference(args):
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    try:
+        import run_ref
+
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        par = args.parallelism if world > 1 or args.parallelism != "ddp" else "ddp"
+        extra = []
+        if par == "2d":
+            extra = ["-tp", str(args.tensor_parallel or 4)]
+        r = run_ref.run_reference(par, args.model, args.gpus, args.steps, args.warmup, args.seq_len, args.batch,
+                                  num_layers=args.layers, extra_args=extra)
+    except Exception as e:  # the contract: never crash the driver on the reference arm
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps({"impl": "reference", "unavailable": f"{type(e).__name__}: {str(e)[:300]}"}), flush=True)
+        return
+    if int(os.environ.get("RANK", "0")) == 0:
+        tokens_bytes = 3 * args.batch * args.seq_len * 8
+        out = {
+            "metric": METRIC, "value": r["tokens_per_s"], "unit": "tokens/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic tokens, random-init weights",
+            "impl": "reference",
+            "config": {"model": args.model + (f"[layers={args.layers}]" if args.layers else ""),
+                       "global_batch": r["dp_size"] * args.batch, "seq_len": args.seq_len,
+                       "parallelism": f"dp{r['dp_size']} ({r['script']})"},
+            "e2e": {"value": r["tokens_per_s"], "unit": "tokens/s", "h2d_bytes_per_step": tokens_bytes,
+                    "d2h_bytes_per_step": 4,
+                    "note": "the reference loop copies each batch H2D and reads loss.item() every step"},
+            "ref_timers_ms_per_step": r["ref_timers_ms_per_step"], "ref_breakdown_ms": r["ref_breakdown_ms"],
+            "peak_alloc_gb": r["peak_alloc_gb"], "install": r["install"],
+        }
+        print(json.dumps(out), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

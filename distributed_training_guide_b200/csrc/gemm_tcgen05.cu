@@ -1,0 +1,321 @@
+// bf16 GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM, operands
+// staged by TMA into 128B-swizzled shared memory), persistent and warp-specialised:
+//
+//   warp 0   TMA producer        (one elected lane)      smem ring: full/empty mbarriers
+//   warp 1   MMA issuer          (one elected lane)      tcgen05.mma 128x256x16 (cta_group::1)
+//                                                        or 256x256x16 across a CTA pair (cta_group::2)
+//   warp 2   TMEM allocator      (512 columns = 2 accumulator stages of 256 fp32 columns)
+//   warps 4-7 epilogue           tcgen05.ld -> bf16 -> global (optionally C += ...), overlapped
+//                                with the next tile's MMAs through the second TMEM stage
+//
+// One kernel serves the three training GEMMs by operand majorness (all tensors row-major):
+//   fwd   Y[T,N]  = X[T,K]  . W[N,K]^T    A K-major,  B K-major
+//   dgrad dX[T,K] = dY[T,N] . W[N,K]      A K-major,  B MN-major
+//   wgrad dW[N,K] = dY[T,N]^T . X[T,K]    A MN-major, B MN-major   (accumulate into the flat grad)
+// This replaces the cuBLAS calls behind every nn.Linear of the reference and its
+// mainloop is what the fused all-gather->GEMM / GEMM->reduce-scatter kernels in fused_tp.cu reuse.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "api.h"
+#include "common.cuh"
+#include "gemm_common.cuh"
+#include "ptx.cuh"
+
+namespace dtg {
+
+using namespace ptx;
+
+template <bool A_K, bool B_K, int CG>
+__global__ void __launch_bounds__(256, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 __nv_bfloat16* __restrict__ C, int M, int N, int K, long long ldc, int accumulate, int num_m_tiles,
+                 int num_tiles) {
+  using Cfg = GemmCfg<CG>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::STAGES;
+  uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x / CG;
+  const int num_clusters = gridDim.x / CG;
+  const int num_kb = (K + Cfg::BK - 1) / Cfg::BK;
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full[i], CG);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4 * CG);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<CG>(tmem_ptr_smem, 512);
+    tmem_relinquish<CG>();
+  }
+  tc_fence_before();
+  if (CG == 2) cluster_sync(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        const int m0 = (t % num_m_tiles) * (Cfg::BM * CG) + (int)cta_rank * Cfg::BM;
+        const int nb = (t / num_m_tiles) * Cfg::BN + (int)cta_rank * Cfg::B_ROWS;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int k0 = kb * Cfg::BK;
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          if constexpr (CG == 1) {
+            mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+            if constexpr (A_K) {
+              tma_load_2d(&tmA, &full[stage], sa, k0, m0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < Cfg::BM / 64; ++j) tma_load_2d(&tmA, &full[stage], sa + j * 8192, m0 + 64 * j, k0);
+            }
+            if constexpr (B_K) {
+              tma_load_2d(&tmB, &full[stage], sb, k0, nb);
+            } else {
+#pragma unroll
+              for (int j = 0; j < Cfg::B_ROWS / 64; ++j) tma_load_2d(&tmB, &full[stage], sb + j * 8192, nb + 64 * j, k0);
+            }
+          } else {
+            const uint32_t bar = mapa(smem_u32(&full[stage]), 0);  // the leader CTA's barrier
+            if (is_leader) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+            else mbar_arrive_cluster(bar);
+            if constexpr (A_K) {
+              tma_load_2d_cg2(&tmA, bar, sa, k0, m0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < Cfg::BM / 64; ++j) tma_load_2d_cg2(&tmA, bar, sa + j * 8192, m0 + 64 * j, k0);
+            }
+            if constexpr (B_K) {
+              tma_load_2d_cg2(&tmB, bar, sb, k0, nb);
+            } else {
+#pragma unroll
+              for (int j = 0; j < Cfg::B_ROWS / 64; ++j) tma_load_2d_cg2(&tmB, bar, sb + j * 8192, nb + 64 * j, k0);
+            }
+          }
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA) =====================
+    if (is_leader && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(Cfg::BM * CG, Cfg::BN, !A_K, !B_K);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * Cfg::BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_base = a_base + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < Cfg::BK / 16; ++k) {
+            const uint64_t da = A_K ? desc_kmajor_sw128(a_base + k * 32) : desc_mnmajor_sw128(a_base + k * 2048, 8192);
+            const uint64_t db = B_K ? desc_kmajor_sw128(b_base + k * 32) : desc_mnmajor_sw128(b_base + k * 2048, 8192);
+            mma_f16_ss<CG>(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          if constexpr (CG == 1) mma_commit(&empty[stage]); else mma_commit_cg2_mc(&empty[stage], 0b11);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        if constexpr (CG == 1) mma_commit(&tmem_full[acc]); else mma_commit_cg2_mc(&tmem_full[acc], 0b11);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int q = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      const int m0 = (t % num_m_tiles) * (Cfg::BM * CG) + (int)cta_rank * Cfg::BM;
+      const int n0 = (t / num_m_tiles) * Cfg::BN;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::BN);
+      __nv_bfloat16* crow = C + (size_t)row * ldc + n0;
+#pragma unroll 1
+      for (int c = 0; c < Cfg::BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + c, r);
+        tmem_ld_wait();
+        if (row < M) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            if (n0 + c + v * 8 < N) {
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[v * 8 + j]);
+              if (accumulate) {
+                float g[8];
+                unpack8(ld8(crow + c + v * 8), g);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] += g[j];
+              }
+              st8(crow + c + v * 8, pack8(f));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CG == 1) mbar_arrive(&tmem_empty[acc]);
+        else mbar_arrive_cluster(mapa(smem_u32(&tmem_empty[acc]), 0));
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  if (CG == 2) cluster_sync(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<CG>(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    DTG_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !p) throw std::runtime_error("cuTensorMapEncodeTiled unavailable");
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                           const uint32_t* box, bool swizzle128) {
+  CUtensorMap m;
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim,
+                               gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    throw std::runtime_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r) +
+                             " (base must be 16B aligned, strides multiples of 16B)");
+  }
+  return m;
+}
+
+CUtensorMap make_tmap_2d(const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes, uint32_t box_inner,
+                         uint32_t box_outer) {
+  uint64_t dims[2] = {inner, outer};
+  uint64_t strides[1] = {row_stride_bytes};
+  uint32_t box[2] = {box_inner, box_outer};
+  return make_tmap_bf16(base, 2, dims, strides, box, true);
+}
+
+static int g_gemm_variant = 0;  // 0 = env/default
+void set_gemm_variant(int v) { g_gemm_variant = v; }
+int default_gemm_variant() {
+  if (g_gemm_variant) return g_gemm_variant;
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("DTG_GEMM_VARIANT");
+    env = e ? atoi(e) : DTG_DEFAULT_GEMM_VARIANT;
+  }
+  return env;
+}
+
+template <bool A_K, bool B_K, int CG>
+static void launch_gemm(const void* A, const void* B, void* C, int M, int N, int K, long long lda, long long ldb,
+                        long long ldc, bool accumulate, cudaStream_t s) {
+  using Cfg = GemmCfg<CG>;
+  const CUtensorMap tmA = A_K ? make_tmap_2d(A, K, M, lda * 2, 64, Cfg::BM) : make_tmap_2d(A, M, K, lda * 2, 64, 64);
+  const CUtensorMap tmB =
+      B_K ? make_tmap_2d(B, K, N, ldb * 2, 64, Cfg::B_ROWS) : make_tmap_2d(B, N, K, ldb * 2, 64, 64);
+  const int num_m_tiles = (M + Cfg::BM * CG - 1) / (Cfg::BM * CG);
+  const int num_n_tiles = (N + Cfg::BN - 1) / Cfg::BN;
+  const int num_tiles = num_m_tiles * num_n_tiles;
+  auto kern = gemm_bf16_kernel<A_K, B_K, CG>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DTG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  int clusters = sm_count() / CG;
+  if (clusters > num_tiles) clusters = num_tiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * CG);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = CG;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  DTG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, (__nv_bfloat16*)C, M, N, K, ldc, accumulate ? 1 : 0,
+                                    num_m_tiles, num_tiles));
+  note_launch();
+}
+
+void gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, long long lda, long long ldb, long long ldc,
+               bool a_kmajor, bool b_kmajor, bool accumulate, int variant, cudaStream_t s) {
+  if (M <= 0 || N <= 0 || K <= 0) return;
+  if ((N % 8) || (ldc % 8) || (lda % 8) || (ldb % 8))
+    throw std::runtime_error("gemm_bf16: N and the leading dimensions must be multiples of 8 elements");
+  if (variant == 0) variant = default_gemm_variant();
+  const int cg = (variant == 2) ? 2 : 1;
+#define DTG_GEMM_CASE(AK, BK)                                                                         \
+  if (a_kmajor == AK && b_kmajor == BK) {                                                             \
+    if (cg == 2) launch_gemm<AK, BK, 2>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, s);               \
+    else launch_gemm<AK, BK, 1>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, s);                       \
+    return;                                                                                           \
+  }
+  DTG_GEMM_CASE(true, true)
+  DTG_GEMM_CASE(true, false)
+  DTG_GEMM_CASE(false, false)
+  DTG_GEMM_CASE(false, true)
+#undef DTG_GEMM_CASE
+}
+
+}  // namespace dtg

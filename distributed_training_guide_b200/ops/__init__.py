@@ -263,6 +263,13 @@ def attention_qkv(qkv, nh, nkv, scale=None):
     if _ext.use_cuda_kernel("attention", qkv) and qkv.dtype == torch.bfloat16 and d == 128:
         return _AttentionQKV.apply(qkv, nh, nkv, scale)
     q, k, v = qkv[:, :, :nh], qkv[:, :, nh:nh + nkv], qkv[:, :, nh + nkv:]
+    if qkv.is_cuda:
+        # head dims other than 128 (GPT-2 style / toy configs) are outside the sm_100a kernel's
+        # scope; use the library kernel rather than the O(S^2)-memory reference
+        o = torch.nn.functional.scaled_dot_product_attention(
+            q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=True, scale=scale,
+            enable_gqa=(nh != nkv))
+        return o.transpose(1, 2)
     return ref.attention(q, k, v, causal=True, scale=scale)
 
 

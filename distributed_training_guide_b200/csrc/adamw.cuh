@@ -28,6 +28,7 @@ inline AdamWHyper make_adamw_hyper(float lr, float beta1, float beta2, float eps
   return h;
 }
 
+#ifdef __CUDACC__
 // torch.optim.AdamW semantics: decoupled decay, bias-corrected moments.
 __device__ __forceinline__ void adamw_update(float& p, float g, float& m, float& v, const AdamWHyper& h) {
   g *= h.grad_scale;
@@ -48,5 +49,7 @@ __device__ __forceinline__ void store_state8(float* s, const float (&f)[8]) {
   reinterpret_cast<float4*>(s)[0] = make_float4(f[0], f[1], f[2], f[3]);
   reinterpret_cast<float4*>(s)[1] = make_float4(f[4], f[5], f[6], f[7]);
 }
+
+#endif  // __CUDACC__
 
 }  // namespace dtg

@@ -39,6 +39,8 @@ void adamw_flat(void* p, const void* g, void* m, void* v, long long n, float lr,
 void gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, long long lda, long long ldb, long long ldc,
                bool a_kmajor, bool b_kmajor, bool accumulate, int variant, cudaStream_t s);
 
+int gemm_max_active_clusters(int cg);
+
 // ---- attention.cu --------------------------------------------------------------------------
 // qkv: [B,S,nh+2*nkv,128] bf16 (q heads | k heads | v heads); o: [B,S,nh,128]; lse: [B,nh,S] fp32
 void attn_fwd(const void* qkv, void* o, float* lse, int B, int S, int nh, int nkv, float scale, cudaStream_t s);

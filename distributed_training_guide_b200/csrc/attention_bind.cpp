@@ -1,0 +1,50 @@
+// Python bindings for the tcgen05 flash-attention kernels.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include "api.h"
+#include "comm_api.h"
+
+namespace dtg {
+namespace {
+using torch::Tensor;
+
+void check_qkv(const Tensor& qkv, int64_t nh, int64_t nkv) {
+  TORCH_CHECK(qkv.is_cuda() && qkv.is_contiguous() && qkv.scalar_type() == at::kBFloat16,
+              "qkv must be a contiguous bf16 CUDA tensor");
+  TORCH_CHECK(qkv.dim() == 4 && qkv.size(2) == nh + 2 * nkv && qkv.size(3) == 128,
+              "qkv must be [B, S, nh+2*nkv, 128]");
+}
+
+std::tuple<Tensor, Tensor> py_attn_fwd(const Tensor& qkv, int64_t nh, int64_t nkv, double scale) {
+  check_qkv(qkv, nh, nkv);
+  const c10::cuda::CUDAGuard guard(qkv.device());
+  const int64_t B = qkv.size(0), S = qkv.size(1);
+  Tensor o = torch::empty({B, S, nh, 128}, qkv.options());
+  Tensor lse = torch::empty({B, nh, S}, qkv.options().dtype(at::kFloat));
+  dtg::attn_fwd(qkv.data_ptr(), o.data_ptr(), lse.data_ptr<float>(), (int)B, (int)S, (int)nh, (int)nkv, (float)scale,
+                at::cuda::getCurrentCUDAStream().stream());
+  return {o, lse};
+}
+
+Tensor py_attn_bwd(const Tensor& d_o, const Tensor& qkv, const Tensor& o, const Tensor& lse, int64_t nh, int64_t nkv,
+                double scale) {
+  check_qkv(qkv, nh, nkv);
+  TORCH_CHECK(d_o.is_contiguous() && o.is_contiguous() && d_o.scalar_type() == at::kBFloat16, "dO/O must be contiguous bf16");
+  const c10::cuda::CUDAGuard guard(qkv.device());
+  const int64_t B = qkv.size(0), S = qkv.size(1);
+  Tensor dqkv = torch::empty_like(qkv);
+  Tensor delta = torch::empty({B, nh, S}, qkv.options().dtype(at::kFloat));
+  dtg::attn_bwd(qkv.data_ptr(), o.data_ptr(), d_o.data_ptr(), lse.data_ptr<float>(), delta.data_ptr<float>(), nullptr,
+                dqkv.data_ptr(), (int)B, (int)S, (int)nh, (int)nkv, (float)scale,
+                at::cuda::getCurrentCUDAStream().stream());
+  return dqkv;
+}
+}  // namespace
+
+void bind_attention(pybind11::module_& m) {
+  m.def("attn_fwd", &py_attn_fwd);
+  m.def("attn_bwd", &py_attn_bwd);
+}
+}  // namespace dtg

@@ -168,6 +168,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("launch_count", []() { return (uint64_t)dtg::launch_count(); });
   m.def("gemm", &gemm, py::arg("a"), py::arg("b"), py::arg("out"), py::arg("trans_a") = false,
         py::arg("trans_b") = false, py::arg("accumulate") = false, py::arg("variant") = 0);
+  m.def("gemm_max_active_clusters", [](int cg) { return dtg::gemm_max_active_clusters(cg); });
   m.def("rmsnorm_fwd", &rmsnorm_fwd);
   m.def("rmsnorm_bwd", &rmsnorm_bwd);
   m.def("rope_inplace", &rope_inplace);
@@ -179,4 +180,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("embedding_bwd", &embedding_bwd);
   m.def("adamw_flat", &adamw_flat);
   dtg::bind_comm(m);
+  dtg::bind_attention(m);
 }

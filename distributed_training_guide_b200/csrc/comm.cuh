@@ -1,0 +1,36 @@
+// Types and launchers of the NVLink symmetric-memory collectives (comm.cu, fused_tp.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+#include "adamw.cuh"
+
+namespace dtg {
+
+constexpr int kMaxRanks = 8;
+constexpr int kMaxChannels = 256;  // one signal-pad channel per CTA of a collective kernel
+constexpr int kCommThreads = 512;
+constexpr long long kSpinTimeoutCycles = 20LL * 1000 * 1000 * 1000;  // ~10 s at 2 GHz
+constexpr size_t kPadBytes = (size_t)kMaxChannels * kMaxRanks * sizeof(uint32_t);
+
+// Base pointers of one symmetric buffer on every rank, ROTATED: ptr[0] = this rank,
+// ptr[k] = rank (rank + k) % nranks.
+struct SymmPtrs {
+  char* ptr[kMaxRanks];
+};
+// Signal pads (NOT rotated: ptr[p] = rank p's pad): uint32 [kMaxChannels][kMaxRanks]
+struct SymmPads {
+  uint32_t* ptr[kMaxRanks];
+};
+
+void comm_allreduce_scale(const SymmPtrs& buf, const SymmPads& pads, size_t elem_off, size_t n, float scale, int rank,
+                          int nranks, uint32_t epoch, int* err, int blocks, cudaStream_t s);
+void comm_rs_adamw(const SymmPtrs& grads, const SymmPtrs& params, void* param_local, void* m, void* v, bool state_fp32,
+                   bool push_params, const SymmPads& pads, size_t elem_off, size_t n, const AdamWHyper& hp, int rank,
+                   int nranks, uint32_t epoch, int* err, int blocks, cudaStream_t s);
+void comm_allgather(const SymmPtrs& shards, void* full, const SymmPads& pads, size_t shard_off, size_t per, int rank,
+                    int nranks, uint32_t epoch, int* err, bool barrier, int blocks, cudaStream_t s);
+void comm_barrier(const SymmPads& pads, int rank, int nranks, uint32_t epoch, int* err, cudaStream_t s);
+
+}  // namespace dtg

@@ -33,7 +33,8 @@ inline int sm_count() {
   return n;
 }
 
-// ---- device-side helpers --------------------------------------------------------------------
+// ---- device-side helpers (nvcc only) ----------------------------------------------------------
+#ifdef __CUDACC__
 struct alignas(16) bf16x8 {
   __nv_bfloat162 v[4];
 };
@@ -87,5 +88,7 @@ __device__ __forceinline__ float block_max(float v, float* red) {
   r = warp_max(r);
   return r;
 }
+
+#endif  // __CUDACC__
 
 }  // namespace dtg

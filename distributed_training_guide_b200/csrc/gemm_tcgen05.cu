@@ -222,6 +222,16 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                            const uint32_t* box, bool swizzle128) {
+  // The driver entry point needs a current context; autograd worker threads may reach this before
+  // any runtime call has bound the primary context to them.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    int dev = 0;
+    DTG_CUDA_CHECK(cudaGetDevice(&dev));
+    DTG_CUDA_CHECK(cudaSetDevice(dev));
+    DTG_CUDA_CHECK(cudaFree(nullptr));
+    ctx_bound = true;
+  }
   CUtensorMap m;
   cuuint64_t gdim[5];
   cuuint64_t gstr[4];
@@ -296,6 +306,34 @@ static void launch_gemm(const void* A, const void* B, void* C, int M, int N, int
   DTG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, (__nv_bfloat16*)C, M, N, K, ldc, accumulate ? 1 : 0,
                                     num_m_tiles, num_tiles));
   note_launch();
+}
+
+// max co-resident clusters of the 2-CTA kernel (diagnostics)
+int gemm_max_active_clusters(int cg) {
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(256);
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = cg;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  int n = -1;
+  if (cg == 2) {
+    auto kern = gemm_bf16_kernel<true, true, 2>;
+    cfg.gridDim = dim3(148);
+    cfg.dynamicSmemBytes = GemmCfg<2>::SMEM_BYTES;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2>::SMEM_BYTES);
+    cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+  } else {
+    auto kern = gemm_bf16_kernel<true, true, 1>;
+    cfg.gridDim = dim3(148);
+    cfg.dynamicSmemBytes = GemmCfg<1>::SMEM_BYTES;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::SMEM_BYTES);
+    cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+  }
+  return n;
 }
 
 void gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, long long lda, long long ldb, long long ldc,

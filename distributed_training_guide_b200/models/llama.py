@@ -205,9 +205,9 @@ class LlamaForCausalLM(nn.Module):
         self.lm_head = Linear(config.hidden_size, vocab_local, dtype, device)
         if config.tie_word_embeddings:
             self.lm_head.weight = self.model.embed_tokens.weight
-        #: hooks the parallel engines use: callables run around each decoder layer
-        self.layer_pre_hooks = []
-        self.layer_post_hooks = []
+        #: parallel engine (parallel/ddp.py, fsdp.py): called around every decoder layer and the
+        #: head so it can insert autograd boundaries, prefetch shards and launch bucket kernels
+        self.engine = None
         self.activation_checkpointing = False
         self.tp = None
 
@@ -246,19 +246,24 @@ class LlamaForCausalLM(nn.Module):
             cos, sin = m.rotary_emb.tables(S, input_ids.device)
         else:
             cos, sin = m.rotary_emb(position_ids)
+        eng = self.engine
+        if eng is not None:
+            eng.pre_forward(self)
         x = m.embed_tokens(input_ids)
         residual = None
-        for layer in m.layers:
-            for hook in self.layer_pre_hooks:
-                hook(layer)
+        for i, layer in enumerate(m.layers):
+            if eng is not None:
+                x, residual = eng.pre_layer(i, layer, x, residual)
             if self.activation_checkpointing and torch.is_grad_enabled():
                 from ..parallel.act_ckpt import checkpoint_layer
 
                 x, residual = checkpoint_layer(layer, x, residual, cos, sin)
             else:
                 x, residual = layer(x, residual, cos, sin)
-            for hook in self.layer_post_hooks:
-                hook(layer)
+            if eng is not None:
+                x, residual = eng.post_layer(i, layer, x, residual)
+        if eng is not None:
+            x, residual = eng.pre_head(x, residual)
         y, _ = m.norm(x, residual)
         logits = self.lm_head(y.reshape(B * S, -1))  # [T, V], a fresh tensor the loss may consume
         loss = None

@@ -1,0 +1,172 @@
+"""Data parallelism with the gradient collective fused into the bucket kernel (chapter 02).
+
+Reference: ``DistributedDataParallel(model, bucket_cap_mb=500, gradient_as_bucket_view=True)`` plus
+``ZeroRedundancyOptimizer(AdamW, fused=True)`` (``02-distributed-data-parallel/train_llm.py:66-68,
+87-89``).  There, torch's C++ Reducer copies/pre-divides gradients into ≤500 MiB buckets and launches
+one NCCL all-reduce per bucket on a side stream; ZeRO-1 then updates 1/N of the tensors per rank and
+issues ~291 per-tensor NCCL broadcasts that are fully exposed in ``optimizer.step()``.
+
+Here a *bucket* is a flat group (embedding, each decoder layer, head) whose gradients the wgrad
+GEMMs already wrote into one symmetric buffer.  When the autograd boundary in front of a layer
+fires (all of that layer's gradients are final) the engine launches, on a communication stream and
+overlapped with the rest of backward, ONE kernel per bucket:
+
+  * ``zero1=True``  reduce-scatter (pull my 1/N slice from all peers over NVLink) -> 1/N scale ->
+                    AdamW on my optimizer-state shard -> push the updated bf16 parameters into every
+                    replica (``comm.cu: rs_adamw_kernel<PUSH_PARAMS=true>``).  ``optimizer.step()`` then
+                    only joins the communication stream: no all-reduce, no broadcasts.
+  * ``zero1=False`` two-shot all-reduce with the 1/N scale fused (``allreduce_scale_kernel``); the
+                    optimizer then updates the full replica locally (plain DDP).
+
+``no_sync()`` (gradient accumulation, reference related-topics/gradient-accumulation) skips the
+bucket kernels on non-boundary micro-batches; the wgrad GEMMs keep accumulating in place.
+On CPU (gloo tests) the same engine falls back to ``torch.distributed`` collectives.
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+from torch.autograd import Variable
+
+from .flat import FlatGroup
+from .optim import FlatAdamW
+
+
+class _Boundary(torch.autograd.Function):
+    """Identity in forward; in backward, runs ``callback()`` once the gradients of everything
+    downstream of this point (i.e. the whole layer behind it) have been produced."""
+
+    @staticmethod
+    def forward(ctx, callback, x, residual):
+        ctx.callback = callback
+        ctx.has_res = residual is not None
+        if residual is None:
+            return x.view_as(x)
+        return x.view_as(x), residual.view_as(residual)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        ctx.callback()
+        if ctx.has_res:
+            return None, grads[0], grads[1]
+        return None, grads[0], None
+
+
+def boundary(callback, x, residual):
+    if not torch.is_grad_enabled():
+        return x, residual
+    out = _Boundary.apply(callback, x, residual)
+    if residual is None:
+        return out, None
+    return out
+
+
+class DataParallelEngine:
+    def __init__(self, model, groups: List[FlatGroup], optimizer: FlatAdamW, symm=None, registry=None, pg=None,
+                 zero1: bool = True, world_size: int = 1, rank: int = 0):
+        self.model, self.groups, self.optimizer = model, groups, optimizer
+        self.symm, self.registry, self.pg = symm, registry or {}, pg
+        self.zero1, self.world, self.rank = zero1, world_size, rank
+        self.sync_enabled = True
+        self._in_backward = False
+        self.by_name = {g.name: g for g in groups}
+        self.use_kernels = symm is not None
+        if self.use_kernels:
+            self.comm_stream = torch.cuda.Stream(device=symm.device)
+            self._done = torch.cuda.Event()
+        model.engine = self
+        optimizer.external_step = self._optimizer_step
+        self._pending = []  # buckets reduced this step (for the CPU fallback's deferred update)
+
+    # -- hooks called by the model ---------------------------------------------------------------
+    def pre_forward(self, model):
+        pass
+
+    def pre_layer(self, i, layer, x, residual):
+        g = getattr(layer, "_flat_group", None)
+        if g is None:
+            return x, residual
+        return boundary(lambda g=g: self._bucket_ready(g), x, residual)
+
+    def post_layer(self, i, layer, x, residual):
+        return x, residual
+
+    def pre_head(self, x, residual):
+        g = self.by_name.get("head")
+        if g is None:
+            return x, residual
+        return boundary(lambda g=g: self._bucket_ready(g), x, residual)
+
+    # -- gradient synchronisation ---------------------------------------------------------------------
+    @contextlib.contextmanager
+    def no_sync(self):
+        old, self.sync_enabled = self.sync_enabled, False
+        try:
+            yield
+        finally:
+            self.sync_enabled = old
+
+    def _bucket_ready(self, g: FlatGroup):
+        if not self._in_backward:
+            self._in_backward = True
+            Variable._execution_engine.queue_callback(self._finalize_backward)
+        if self.sync_enabled:
+            self._launch(g)
+
+    def _finalize_backward(self):
+        self._in_backward = False
+        if not self.sync_enabled:
+            return
+        g = self.by_name.get("embed")
+        if g is not None:
+            self._launch(g)  # the embedding gradient is only complete at the very end of backward
+        if self.use_kernels:
+            self._done.record(self.comm_stream)
+
+    def _launch(self, g: FlatGroup):
+        opt = self.optimizer
+        if not self.use_kernels:
+            self._launch_fallback(g)
+            return
+        ev = torch.cuda.Event()
+        ev.record()  # on the compute stream: this bucket's wgrad kernels are all enqueued before it
+        gbuf = self.registry[g.grad.data_ptr()]
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ev)
+            if self.zero1:
+                st = opt.state[g.param]
+                st["step"] += 1
+                pbuf = self.registry[g.param.data_ptr()]
+                self.symm.rs_adamw_(gbuf, pbuf, None, st["exp_avg"], st["exp_avg_sq"], True, 0, g.padded_numel,
+                                    opt.hyper(), st["step"], opt.grad_scale / self.world)
+            else:
+                self.symm.allreduce_scale_(gbuf, 0, g.padded_numel, 1.0 / self.world)
+
+    def _launch_fallback(self, g: FlatGroup):
+        """torch.distributed path (CPU / gloo): all-reduce now, sharded update in optimizer.step()."""
+        if self.world > 1:
+            buf = g.grad.float()
+            dist.all_reduce(buf, group=self.pg)
+            g.grad.copy_((buf / self.world).to(g.grad.dtype))
+        self._pending.append(g)
+
+    # -- optimizer step ---------------------------------------------------------------------------------
+    def _optimizer_step(self):
+        opt = self.optimizer
+        if self.use_kernels:
+            torch.cuda.current_stream().wait_event(self._done)  # join the communication stream
+            if not self.zero1:
+                for g in self.groups:
+                    opt.step_group(g)
+            return
+        for g in self.groups:
+            opt.step_group(g)  # on its shard when ZeRO-1 (optimizer built with shard=(rank, world))
+            if self.zero1 and self.world > 1:
+                lo, hi = g.shard_range(self.rank, self.world)
+                shards = [torch.empty(hi - lo, dtype=torch.float32) for _ in range(self.world)]
+                dist.all_gather(shards, g.param[lo:hi].float(), group=self.pg)
+                g.param.copy_(torch.cat(shards).to(g.param.dtype))
+        self._pending.clear()

@@ -130,5 +130,80 @@ class SingleDevice(Strategy):
 
     def build_model(self, args, config):
         model = build_model(config, dtype=self.dtype(), device=self.env.device)
-        self.groups = build_groups(model, self.env.device, self.dtype())
+        self.groups, self.symm, self.registry = _flat_groups_on(self, model, 1)
         return model
+
+    def build_optimizer(self, args, model, lr):
+        opt = FlatAdamW(self.groups, lr=lr)
+        if self.symm is not None and hasattr(model, "engine"):
+            # one rank, same engine: AdamW of each bucket runs inside backward on a side stream as soon
+            # as that bucket's gradients are final (the N=1 case of the fused reduce-scatter+AdamW kernel)
+            from .ddp import DataParallelEngine
+
+            self.engine = DataParallelEngine(model, self.groups, opt, symm=self.symm, registry=self.registry,
+                                             zero1=True, world_size=1, rank=0)
+        return opt
+
+    def grad_sync(self, model, enabled=True):
+        eng = getattr(self, "engine", None)
+        if enabled or eng is None:
+            return contextlib.nullcontext()
+        return eng.no_sync()
+
+
+def _flat_groups_on(strategy, model, world_size=1, pg=None):
+    """Flat param/grad buffers for ``model``: NVLink-symmetric on CUDA, plain tensors on CPU.
+    Returns (groups, symm_group_or_None, registry)."""
+    from . import symm as symm_mod
+
+    device = strategy.env.device
+    if device.type == "cuda":
+        sg = symm_mod.SymmGroup(device, pg=pg) if (world_size > 1 or pg is not None) else symm_mod.SymmGroup(device, ranks=[0])
+        registry = {}
+        groups = build_groups(model, device, strategy.dtype(), world_size=world_size, alloc=sg.allocator(registry))
+        return groups, sg, registry
+    return build_groups(model, device, strategy.dtype(), world_size=world_size), None, {}
+
+
+class DataParallelZero1(Strategy):
+    """Chapter 02: DDP + ZeRO-1 with the bucket collective fused into one NVLink kernel
+    (``parallel/ddp.py``).  ``zero1=False`` gives plain DDP (fused scale + all-reduce)."""
+
+    chapter = "02-distributed-data-parallel"
+
+    def __init__(self, args=None, zero1: bool = True):
+        super().__init__(args)
+        self.zero1 = zero1
+        self.engine = None
+        self.symm = None
+
+    def build_model(self, args, config):
+        env = self.env
+        with self.data_guard():
+            model = build_model(config, dtype=self.dtype(), device=env.device)
+        self.groups, self.symm, self.registry = _flat_groups_on(self, model, env.world_size)
+        if env.distributed and env.world_size > 1:
+            for g in self.groups:  # replicas must start identical (torch DDP broadcasts in its ctor, N1)
+                dist.broadcast(g.param, src=0)
+        self.model = model
+        return model
+
+    def build_optimizer(self, args, model, lr):
+        from .ddp import DataParallelEngine
+
+        env = self.env
+        shard = (env.rank, env.world_size) if (self.zero1 and env.world_size > 1) else None
+        opt = FlatAdamW(self.groups, lr=lr, shard=shard)
+        self.engine = DataParallelEngine(model, self.groups, opt, symm=self.symm, registry=self.registry,
+                                         zero1=self.zero1, world_size=env.world_size, rank=env.rank)
+        return opt
+
+    def grad_sync(self, model, enabled=True):
+        if enabled or self.engine is None:
+            return contextlib.nullcontext()
+        return self.engine.no_sync()
+
+    def teardown(self):
+        if self.symm is not None:
+            torch.cuda.synchronize()
+            self.symm.check()

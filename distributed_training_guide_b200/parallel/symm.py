@@ -1,0 +1,137 @@
+"""NVLink symmetric memory: buffers every rank of a group can address directly.
+
+This is the substrate the reference does not have (it only ever calls NCCL):
+each rank ``cudaMalloc``s the same size outside the caching allocator, exports a CUDA-IPC handle,
+handles are exchanged once through ``torch.distributed`` (NCCL/gloo is used for this bootstrap
+only), and every rank maps its peers' buffers.  Collective *kernels* (``csrc/comm.cu``,
+``csrc/fused_tp.cu``) then load/store peer memory over NVLink 5 / NVSwitch and synchronise with
+device-side epoch flags in a symmetric signal pad — no host round trips, no NCCL on the hot path.
+
+``SymmGroup`` also runs on a single rank (N = 1: same kernels, no peers), which is how the
+single-GPU chapter shares the fused optimizer path.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .. import _ext
+
+_LIVE_GROUPS = []
+
+
+def allocated_bytes() -> int:
+    c = _ext.load(False)
+    return int(c.symm_allocated_bytes()) if c is not None and hasattr(c, "symm_allocated_bytes") else 0
+
+
+class SymmBuffer:
+    """One symmetric allocation: ``local`` (this rank's memory as a tensor) + every rank's base pointer."""
+
+    def __init__(self, local: torch.Tensor, ptrs: List[int], raw: torch.Tensor):
+        self.local = local
+        self.ptrs = ptrs
+        self._raw = raw  # keeps the cudaMalloc alive
+
+    def elem_offset_of(self, view: torch.Tensor) -> int:
+        off = view.data_ptr() - self.local.data_ptr()
+        assert off >= 0 and off % view.element_size() == 0
+        return off // view.element_size()
+
+
+class SymmGroup:
+    def __init__(self, device: torch.device, pg=None, ranks: Optional[List[int]] = None, comm_blocks: int = 32):
+        self.C = _ext.load(required=True)
+        self.device = torch.device(device)
+        self.pg = pg
+        if dist.is_initialized() and (pg is not None or ranks is None):
+            self.world = dist.get_world_size(pg)
+            self.rank = dist.get_rank(pg)
+        else:
+            self.world, self.rank = 1, 0
+        if self.world not in (1, 2, 4, 8):
+            raise ValueError(f"symmetric collectives support 1/2/4/8 ranks, got {self.world}")
+        self.comm_blocks = min(comm_blocks, int(self.C.SYMM_MAX_CHANNELS))
+        self._peer_handles = []
+        self.epoch = 0
+        self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.pads = self.alloc_bytes(int(self.C.SYMM_PAD_BYTES))
+        self.pad_ptrs = self.pads.ptrs
+        _LIVE_GROUPS.append(self)
+
+    # -- allocation -----------------------------------------------------------------------------
+    def alloc_bytes(self, nbytes: int) -> SymmBuffer:
+        raw, handle = self.C.symm_alloc(int(nbytes), self.device.index or 0)
+        if self.world == 1:
+            ptrs = [raw.data_ptr()]
+        else:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle), group=self.pg)
+            ptrs = []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    ptrs.append(raw.data_ptr())
+                else:
+                    p = self.C.symm_open(h, self.device.index or 0)
+                    self._peer_handles.append(p)
+                    ptrs.append(p)
+            dist.barrier(group=self.pg)
+        return SymmBuffer(raw, ptrs, raw)
+
+    def alloc(self, numel: int, dtype: torch.dtype) -> SymmBuffer:
+        esize = torch.empty((), dtype=dtype).element_size()
+        b = self.alloc_bytes(numel * esize)
+        b.local = b._raw[: numel * esize].view(dtype)
+        return b
+
+    def allocator(self, registry: dict):
+        """An ``alloc(n, dtype) -> tensor`` callable for ``flat.build_groups`` that records the
+        SymmBuffer of each returned tensor in ``registry[data_ptr]``."""
+
+        def alloc(n, dtype):
+            b = self.alloc(n, dtype)
+            registry[b.local.data_ptr()] = b
+            return b.local
+
+        return alloc
+
+    # -- collectives ------------------------------------------------------------------------------
+    def _epochs(self, n: int = 2) -> int:
+        e = self.epoch + 1
+        self.epoch += n
+        return e
+
+    def allreduce_scale_(self, buf: SymmBuffer, elem_off: int, n: int, scale: float, blocks: Optional[int] = None):
+        self.C.comm_allreduce_scale(buf.ptrs, self.pad_ptrs, elem_off, n, scale, self.rank, self._epochs(2), self.err,
+                                    blocks or self.comm_blocks)
+
+    def rs_adamw_(self, grads: SymmBuffer, params: Optional[SymmBuffer], param_local, m, v, push_params: bool,
+                  elem_off: int, n: int, hyper, step: int, grad_scale: float, blocks: Optional[int] = None):
+        lr, b1, b2, eps, wd = hyper
+        self.C.comm_rs_adamw(grads.ptrs, params.ptrs if params is not None else [], param_local, m, v, push_params,
+                             self.pad_ptrs, elem_off, n, lr, b1, b2, eps, wd, step, grad_scale, self.rank,
+                             self._epochs(2), self.err, blocks or self.comm_blocks)
+
+    def allgather_(self, shards: SymmBuffer, full: torch.Tensor, shard_off: int, per: int, barrier: bool = True,
+                   blocks: Optional[int] = None):
+        self.C.comm_allgather(shards.ptrs, full, self.pad_ptrs, shard_off, per, self.rank, self._epochs(1), self.err,
+                              barrier, blocks or self.comm_blocks)
+
+    def barrier_(self):
+        self.C.comm_barrier(self.pad_ptrs, self.rank, self._epochs(1), self.err)
+
+    def check(self):
+        """Raise if a device-side barrier timed out (a peer died or diverged)."""
+        v = int(self.err.item())
+        if v:
+            raise RuntimeError(f"NVLink barrier timed out waiting for rank {v - 1} (group rank {self.rank})")
+
+    def close(self):
+        for p in self._peer_handles:
+            try:
+                self.C.symm_close(p)
+            except Exception:
+                pass
+        self._peer_handles = []

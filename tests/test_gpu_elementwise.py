@@ -39,7 +39,7 @@ def test_rmsnorm_fwd_bwd(T, H, with_res):
     wf = w.detach().float().requires_grad_(True)
     hf = xf + rf if with_res else xf
     if with_res:
-        hf = hf.to(torch.bfloat16).float() + (hf - hf.detach())  # the residual stream is rounded to bf16
+        hf = hf + (hf.to(torch.bfloat16).float() - hf).detach()  # the residual stream is rounded to bf16
     yf = hf * torch.rsqrt(hf.pow(2).mean(-1, keepdim=True) + 1e-5) * wf
     loss = (yf * dy.float()).sum()
     if with_res:

@@ -9,7 +9,7 @@ nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm,power.draw --format=cs
 for f in $FILES; do
   name=$(basename "$f" .py)
   echo "=== $f"
-  timeout --signal=KILL ${DTG_TEST_TIMEOUT:-600} python -m pytest "$f" -m gpu -x -q --no-header -p no:cacheprovider \
+  timeout --signal=KILL ${DTG_TEST_TIMEOUT:-600} python -m pytest "$f" -m gpu -q --no-header -p no:cacheprovider \
     > "gpurun_out/${name}.log" 2>&1
   echo "exit=$?" >> "gpurun_out/${name}.log"
   tail -n 15 "gpurun_out/${name}.log"

@@ -155,6 +155,25 @@ __global__ void __launch_bounds__(kCommThreads) allgather_kernel(SymmPtrs shards
   }
 }
 
+// ---- plain reduce-scatter (mean) into a local shard: used when the optimizer runs elsewhere (CPU offload) ----
+template <int NR>
+__global__ void __launch_bounds__(kCommThreads) reduce_scatter_kernel(SymmPtrs grads, __nv_bfloat16* out, SymmPads pads,
+                                                                      size_t elem_off, size_t n, float scale, int rank,
+                                                                      uint32_t epoch, int* err) {
+  symm_barrier(pads.ptr, rank, NR, blockIdx.x, epoch, err);
+  const size_t per = n / NR;
+  const size_t base = (elem_off + (size_t)rank * per) * 2;
+  const size_t nvec = per / 8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    float acc[8];
+    gather_sum<NR>(grads, base + i * 16, rank, acc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= scale;
+    *reinterpret_cast<uint4*>(out + i * 8) = pack8_u4(acc);
+  }
+  symm_barrier(pads.ptr, rank, NR, blockIdx.x, epoch + 1, err);
+}
+
 __global__ void barrier_kernel(SymmPads pads, int rank, int nranks, uint32_t epoch, int* err) {
   symm_barrier(pads.ptr, rank, nranks, blockIdx.x, epoch, err);
 }
@@ -208,6 +227,15 @@ void comm_allgather(const SymmPtrs& shards, void* full, const SymmPads& pads, si
   DTG_NR_DISPATCH(nranks, (allgather_kernel<NR><<<blocks, kCommThreads, 0, s>>>(shards, (__nv_bfloat16*)full, pads,
                                                                                shard_off, per, rank, epoch, err,
                                                                                barrier ? 1 : 0)));
+  note_launch();
+  DTG_LAUNCH_CHECK();
+}
+
+void comm_reduce_scatter(const SymmPtrs& grads, void* out, const SymmPads& pads, size_t elem_off, size_t n, float scale,
+                         int rank, int nranks, uint32_t epoch, int* err, int blocks, cudaStream_t s) {
+  check_geometry(n, nranks, blocks);
+  DTG_NR_DISPATCH(nranks, (reduce_scatter_kernel<NR><<<blocks, kCommThreads, 0, s>>>(
+                              grads, (__nv_bfloat16*)out, pads, elem_off, n, scale, rank, epoch, err)));
   note_launch();
   DTG_LAUNCH_CHECK();
 }

@@ -121,6 +121,15 @@ void allgather(const std::vector<uint64_t>& shards, Tensor& full, const std::vec
                  (int)shards.size(), (uint32_t)epoch, err_ptr(err), barrier, (int)blocks, stream());
 }
 
+void reduce_scatter(const std::vector<uint64_t>& grads, Tensor& out, const std::vector<uint64_t>& pads, int64_t elem_off,
+                    int64_t n, double scale, int64_t rank, int64_t epoch, const c10::optional<Tensor>& err,
+                    int64_t blocks) {
+  TORCH_CHECK(out.is_contiguous() && out.scalar_type() == at::kBFloat16 && out.numel() * (int64_t)grads.size() == n,
+              "out must be a contiguous bf16 shard of n / nranks elements");
+  comm_reduce_scatter(rotated(grads, (int)rank), out.data_ptr(), pads_of(pads), (size_t)elem_off, (size_t)n,
+                      (float)scale, (int)rank, (int)grads.size(), (uint32_t)epoch, err_ptr(err), (int)blocks, stream());
+}
+
 void barrier(const std::vector<uint64_t>& pads, int64_t rank, int64_t epoch, const c10::optional<Tensor>& err) {
   comm_barrier(pads_of(pads), (int)rank, (int)pads.size(), (uint32_t)epoch, err_ptr(err), stream());
 }
@@ -137,6 +146,7 @@ void bind_comm(pybind11::module_& m) {
   m.def("comm_allreduce_scale", &allreduce_scale);
   m.def("comm_rs_adamw", &rs_adamw);
   m.def("comm_allgather", &allgather);
+  m.def("comm_reduce_scatter", &reduce_scatter);
   m.def("comm_barrier", &barrier);
 }
 }  // namespace dtg

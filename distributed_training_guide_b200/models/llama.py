@@ -30,6 +30,28 @@ from ..ops import reference as ref
 from .configs import ModelConfig
 
 
+def _name_seed(seed: int, name: str) -> int:
+    import zlib
+
+    return (int(seed) * 1000003 + zlib.crc32(name.encode())) % (2**63 - 1)
+
+
+@torch.no_grad()
+def init_parameter_(p, name: str, seed: int, std: float = 0.02, full_shape=None, shard_dim=None, shard_index=0,
+                    shard_count=1):
+    """Fill ``p`` (possibly a tensor-parallel slice of a ``full_shape`` parameter) deterministically."""
+    if name.endswith("norm.weight") or name.endswith("layernorm.weight"):
+        p.fill_(1.0)
+        return
+    gen = torch.Generator(device=p.device)
+    gen.manual_seed(_name_seed(seed, name))
+    shape = tuple(full_shape) if full_shape is not None else tuple(p.shape)
+    full = torch.empty(shape, dtype=torch.float32, device=p.device).normal_(0.0, std, generator=gen)
+    if shard_dim is not None and shard_count > 1:
+        full = full.chunk(shard_count, dim=shard_dim)[shard_index]
+    p.copy_(full.to(p.dtype))
+
+
 class Linear(nn.Module):
     """Bias-free projection holding ``weight`` [out, in] (HF naming)."""
 
@@ -213,16 +235,16 @@ class LlamaForCausalLM(nn.Module):
 
     # -- initialisation -----------------------------------------------------------------
     @torch.no_grad()
-    def init_weights(self, std: float = 0.02):
-        """Random init (normal(0, 0.02) matrices, unit norm gains), parameter by parameter in
-        ``named_parameters`` order so a given seed gives the same weights on any layout."""
+    def init_weights(self, std: float = 0.02, seed: Optional[int] = None):
+        """Random init: normal(0, 0.02) matrices, unit norm gains.  Every parameter draws from its
+        own generator seeded by (seed, parameter name), so the same seed gives the same weights under
+        any placement: replicated, flat-sharded (FSDP builds one layer at a time) or tensor-parallel
+        (each rank generates the full tensor and keeps its slice)."""
+        seed = torch.initial_seed() if seed is None else seed
+        self._init_seed = seed
         for name, p in self.named_parameters():
-            if p.is_meta:
-                continue
-            if name.endswith("norm.weight") or name.endswith("layernorm.weight"):
-                p.fill_(1.0)
-            else:
-                p.normal_(mean=0.0, std=std)
+            if not p.is_meta:
+                init_parameter_(p, name, seed, std)
 
     def num_parameters(self) -> int:
         return sum(p.numel() for p in self.parameters())

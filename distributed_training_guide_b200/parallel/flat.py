@@ -57,7 +57,10 @@ class FlatGroup:
                 view = self.param[o:o + p.numel()].view(p.shape)
                 if not p.is_meta:
                     view.copy_(p.data)
-                p.data = view
+                    p.data = view
+                else:
+                    # meta-device construction (FSDP): give the parameter object real storage in place
+                    torch.utils.swap_tensors(p, nn.Parameter(view, requires_grad=p.requires_grad))
                 if with_grad:
                     g = self.grad[o:o + p.numel()].view(p.shape)
                     p._dtg_grad = g

@@ -207,3 +207,80 @@ class DataParallelZero1(Strategy):
         if self.symm is not None:
             torch.cuda.synchronize()
             self.symm.check()
+
+
+class FullyShardedDataParallel(Strategy):
+    """Chapters 04 / 05: ZeRO-3 over the data-parallel group with NVLink pull-unshard and the fused
+    reduce-scatter + AdamW kernel (``parallel/fsdp.py``); meta-device construction, optional CPU
+    offload of the optimizer, activation checkpointing and explicit prefetch flags."""
+
+    chapter = "04-fully-sharded-data-parallel"
+
+    def __init__(self, args=None):
+        super().__init__(args)
+        self.engine = None
+        self.symm = None
+
+    def build_model(self, args, config):
+        from . import symm as symm_mod
+        from .fsdp import FSDPEngine
+
+        env = self.env
+        with self.data_guard():
+            model = build_model(config, dtype=self.dtype(), device="meta", init=False)
+        if env.device.type == "cuda":
+            self.symm = symm_mod.SymmGroup(env.device) if env.world_size > 1 else symm_mod.SymmGroup(env.device, ranks=[0])
+        self.engine = FSDPEngine(model, env, self.dtype(), symm=self.symm, world_size=env.world_size, rank=env.rank,
+                                 seed=getattr(args, "seed", 0), cpu_offload=getattr(args, "cpu_offload", False),
+                                 prefetch=True)
+        model.activation_checkpointing = bool(getattr(args, "checkpoint_activations", False))
+        self.groups = self.engine.groups
+        self.model = model
+        return model
+
+    def num_parameters(self, model):
+        return model.config.num_parameters()
+
+    def build_optimizer(self, args, model, lr):
+        return self.engine.build_optimizer(lr)
+
+    def pre_step(self, model):
+        self.engine.pre_step()
+
+    def save_checkpoint(self, exp_dir, model, optimizer, lr_scheduler, state):
+        env = self.env
+        ws = env.world_size if env.distributed else 1
+        if env.device.type == "cuda":
+            torch.cuda.synchronize()
+        ckpt_utils.save_sharded(exp_dir, self.engine.sharded_state(), lr_scheduler, state, env.rank, ws)
+        if env.rank == 0:
+            import json
+
+            with open(Path(exp_dir) / "optimizer_steps.json", "w") as fp:
+                json.dump(self.engine.optimizer_steps(), fp)
+        self.barrier()
+
+    def load_checkpoint(self, exp_dir, model, optimizer, lr_scheduler):
+        import json
+
+        env = self.env
+        ws = env.world_size if env.distributed else 1
+        st = ckpt_utils.load_sharded(exp_dir, self.engine.sharded_state(), lr_scheduler, env.device, env.rank, ws)
+        steps_file = Path(exp_dir) / "optimizer_steps.json"
+        if steps_file.exists():
+            self.engine.set_optimizer_steps(json.loads(steps_file.read_text()))
+        return st
+
+    def make_experiment_dir(self, exp_dir: Path):
+        # shared mount: global rank 0 creates it; node-local disk: each node's local rank 0 (reference 04:162-168)
+        creator = self.env.rank == 0 if exp_dir.parent.is_mount() or self.env.world_size == 1 else self.env.local_rank == 0
+        if creator:
+            LOGGER.info("Creating experiment root directory")
+            exp_dir.mkdir(parents=True, exist_ok=True)
+        self.barrier()
+        (exp_dir / f"rank-{self.env.rank}").mkdir(parents=True, exist_ok=True)  # per-rank dir (reference 04:170-172)
+
+    def teardown(self):
+        if self.symm is not None:
+            torch.cuda.synchronize()
+            self.symm.check()

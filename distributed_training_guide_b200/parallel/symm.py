@@ -119,6 +119,11 @@ class SymmGroup:
         self.C.comm_allgather(shards.ptrs, full, self.pad_ptrs, shard_off, per, self.rank, self._epochs(1), self.err,
                               barrier, blocks or self.comm_blocks)
 
+    def reduce_scatter_(self, grads: SymmBuffer, out: torch.Tensor, elem_off: int, n: int, scale: float,
+                        blocks: Optional[int] = None):
+        self.C.comm_reduce_scatter(grads.ptrs, out, self.pad_ptrs, elem_off, n, scale, self.rank, self._epochs(2),
+                                   self.err, blocks or self.comm_blocks)
+
     def barrier_(self):
         self.C.comm_barrier(self.pad_ptrs, self.rank, self._epochs(1), self.err)
 

@@ -66,7 +66,7 @@ def test_rope_inplace(B, S, nh, nkv, d, per_token):
     out = ops.rope_qkv_(g * 1.0, cos, sin, nh + nkv)
     _close(out, want, 2e-2, 2e-2, "rope")
     dout = torch.randn_like(out)
-    out.backward(dout)
+    out.backward(dout.clone())  # the op rotates its incoming gradient in place (it owns it in the model)
     want_g = torch.cat([ref.rope_apply(dout[:, :, :nh + nkv], cos, sin, inverse=True), dout[:, :, nh + nkv:]], dim=2)
     _close(g.grad, want_g, 2e-2, 2e-2, "rope bwd")
 

@@ -40,6 +40,10 @@ void gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, long 
                bool a_kmajor, bool b_kmajor, bool accumulate, int variant, cudaStream_t s);
 
 int gemm_max_active_clusters(int cg);
+// tensor-parallel variants over symmetric buffers (see gemm_tcgen05.cu)
+void gemm_bf16_dist(int mode, const void* const* a_srcs, const void* const* b_srcs, void* const* c_dsts, int M, int N,
+                    int K, long long lda, long long ldb, long long ldc, bool b_kmajor, bool accumulate, int nranks,
+                    int rank, int rows_per_peer, cudaStream_t s);
 
 // ---- attention.cu --------------------------------------------------------------------------
 // qkv: [B,S,nh+2*nkv,128] bf16 (q heads | k heads | v heads); o: [B,S,nh,128]; lse: [B,nh,S] fp32

@@ -41,6 +41,7 @@ constexpr int OFF_BAR = OFF_DS + 128 * 128;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 constexpr uint32_t TM_S = 0, TM_DP = 128, TM_ACC_A = 256, TM_ACC_B = 384;
 constexpr float LOG2E = 1.4426950408889634f;
+constexpr int THREADS = 384;  // 4 control warps + 8 compute warps (two threads per row)
 }  // namespace bwd
 
 // delta[b, h, s] = sum_d dO * O   (one warp per (token, head) row)
@@ -67,7 +68,7 @@ __global__ void attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ d_o, con
 }
 
 template <bool KV_MODE>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(bwd::THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_constant__ CUtensorMap tm_qkv_c,
                 const __grid_constant__ CUtensorMap tm_do_r, const __grid_constant__ CUtensorMap tm_do_c,
                 const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
@@ -113,9 +114,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       mbar_init(&y_full[i], 1);
       mbar_init(&y_empty[i], 1);
       mbar_init(&sdp_full[i], 1);
-      mbar_init(&sdp_empty[i], 4);
+      mbar_init(&sdp_empty[i], 8);
     }
-    mbar_init(pds_full, 4);
+    mbar_init(pds_full, 8);
     mbar_init(pds_empty, 1);
     fence_barrier_init();
   }
@@ -218,7 +219,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       }
     }
   } else if (warp >= 4) {
-    const int q = warp - 4;
+    // two threads per row: each owns 32 of the 64 columns of a block (and 64 of the 128 output columns)
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
     const int r = q * 32 + lane;  // row inside R == TMEM lane
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const float sl2 = scale * LOG2E;
@@ -228,55 +231,60 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       lse_r = lse[idx] * LOG2E;
       delta_r = delta[idx];
     }
-    uint8_t* sp = smem + OFF_P;
-    uint8_t* sds = smem + OFF_DS;
+    uint8_t* sp = smem + OFF_P + r * 128;
+    uint8_t* sds = smem + OFF_DS + r * 128;
     for (int t = 0; t < n_iter; ++t) {
       const int st = t & 1;
       const int c = c_start + (KV_MODE ? t % n_c : t);
-      const int C0 = c * 64;
-      const float* lse_c = nullptr;
-      const float* delta_c = nullptr;
-      if (KV_MODE) {
+      const int C0 = c * 64 + half * 32;  // first column I own
+      float lq[32], dq[32];
+      if (KV_MODE) {  // per-column statistics of the 32 queries I own (same addresses across the warp)
         const int qh = kv_head * group + t / n_c;
-        lse_c = lse + ((long long)batch * nh + qh) * S + C0;
-        delta_c = delta + ((long long)batch * nh + qh) * S + C0;
+        const float4* lp = reinterpret_cast<const float4*>(lse + ((long long)batch * nh + qh) * S + C0);
+        const float4* dp = reinterpret_cast<const float4*>(delta + ((long long)batch * nh + qh) * S + C0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 a = __ldg(lp + i), b = __ldg(dp + i);
+          lq[4 * i] = a.x * LOG2E; lq[4 * i + 1] = a.y * LOG2E; lq[4 * i + 2] = a.z * LOG2E; lq[4 * i + 3] = a.w * LOG2E;
+          dq[4 * i] = b.x; dq[4 * i + 1] = b.y; dq[4 * i + 2] = b.z; dq[4 * i + 3] = b.w;
+        }
       }
       mbar_wait(&sdp_full[st], (uint32_t)((t >> 1) & 1));
       tc_fence_after();
-      uint32_t pk_p[32], pk_ds[32];  // 64 bf16 each
-#pragma unroll
-      for (int hc = 0; hc < 2; ++hc) {
-        uint32_t rs[32], rd[32];
-        tmem_ld_32x32b_x32(lane_addr + TM_S + st * 64 + hc * 32, rs);
-        tmem_ld_32x32b_x32(lane_addr + TM_DP + st * 64 + hc * 32, rd);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float pv[2], dv[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int col = hc * 32 + i + e;
-            const float lq = KV_MODE ? __ldg(lse_c + col) * LOG2E : lse_r;
-            const float dq = KV_MODE ? __ldg(delta_c + col) : delta_r;
-            // causal: query index >= key index
-            const bool ok = KV_MODE ? (C0 + col >= R0 + r) : (R0 + r >= C0 + col);
-            const float p = ok ? exp2f(__uint_as_float(rs[i + e]) * sl2 - lq) : 0.f;
-            pv[e] = p;
-            dv[e] = p * (__uint_as_float(rd[i + e]) - dq) * scale;
-          }
-          __nv_bfloat162 a = __floats2bfloat162_rn(pv[0], pv[1]);
-          __nv_bfloat162 b = __floats2bfloat162_rn(dv[0], dv[1]);
-          pk_p[(hc * 32 + i) >> 1] = *reinterpret_cast<uint32_t*>(&a);
-          pk_ds[(hc * 32 + i) >> 1] = *reinterpret_cast<uint32_t*>(&b);
-        }
-      }
+      uint32_t rs[32], rd[32];
+      tmem_ld_32x32b_x32(lane_addr + TM_S + st * 64 + half * 32, rs);
+      tmem_ld_32x32b_x32(lane_addr + TM_DP + st * 64 + half * 32, rd);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sdp_empty[st]);
+      // causal: query index >= key index.  Only blocks that touch the diagonal need the compare.
+      const bool need_mask = KV_MODE ? (C0 < R0 + 127) : (C0 + 31 > R0);
+      uint32_t pk_p[16], pk_ds[16];  // 32 bf16 each
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        float pv[2], dv[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float l2 = KV_MODE ? lq[i + e] : lse_r;
+          const float dl = KV_MODE ? dq[i + e] : delta_r;
+          float p = fast_exp2(fmaf(__uint_as_float(rs[i + e]), sl2, -l2));
+          if (need_mask) {
+            const bool ok = KV_MODE ? (C0 + i + e >= R0 + r) : (R0 + r >= C0 + i + e);
+            p = ok ? p : 0.f;
+          }
+          pv[e] = p;
+          dv[e] = p * (__uint_as_float(rd[i + e]) - dl) * scale;
+        }
+        __nv_bfloat162 a = __floats2bfloat162_rn(pv[0], pv[1]);
+        __nv_bfloat162 b = __floats2bfloat162_rn(dv[0], dv[1]);
+        pk_p[i >> 1] = *reinterpret_cast<uint32_t*>(&a);
+        pk_ds[i >> 1] = *reinterpret_cast<uint32_t*>(&b);
+      }
       if (t > 0) mbar_wait(pds_empty, (uint32_t)((t - 1) & 1));  // gradient MMAs of t-1 released P / dS
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {  // 8 chunks of 8 bf16 along the 64-wide row, 128B swizzle
-        const uint32_t off = (uint32_t)(r * 128 + ((ch ^ (r & 7)) << 4));
+      for (int ch = 0; ch < 4; ++ch) {  // my 4 chunks of 8 bf16 inside the 64-wide row, 128B swizzle
+        const uint32_t off = (uint32_t)((((half * 4 + ch) ^ (r & 7))) << 4);
         if (KV_MODE)
           *reinterpret_cast<uint4*>(sp + off) = make_uint4(pk_p[ch * 4], pk_p[ch * 4 + 1], pk_p[ch * 4 + 2], pk_p[ch * 4 + 3]);
         *reinterpret_cast<uint4*>(sds + off) =
@@ -287,16 +295,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
     }
-    // write the accumulated gradients of this row
+    // write the accumulated gradients of this row (my 64 of the 128 columns)
     mbar_wait(pds_empty, (uint32_t)((n_iter - 1) & 1));
     tc_fence_after();
     const long long tok = (long long)batch * S + R0 + r;
     auto write_row = [&](uint32_t tm_col, int out_head) {
-      __nv_bfloat16* dst = dqkv + (tok * nht + out_head) * (long long)D;
+      __nv_bfloat16* dst = dqkv + (tok * nht + out_head) * (long long)D + half * 64;
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
+      for (int cc = 0; cc < 2; ++cc) {
         uint32_t rr[32];
-        tmem_ld_32x32b_x32(lane_addr + tm_col + cc * 32, rr);
+        tmem_ld_32x32b_x32(lane_addr + tm_col + half * 64 + cc * 32, rr);
         tmem_ld_wait();
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
@@ -337,9 +345,9 @@ void attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse,
     attr = true;
   }
   const int nblk = S / 128;
-  attn_bwd_kernel<true><<<dim3(B * nkv, nblk, 1), 256, bwd::SMEM_BYTES, s>>>(
+  attn_bwd_kernel<true><<<dim3(B * nkv, nblk, 1), bwd::THREADS, bwd::SMEM_BYTES, s>>>(
       tq_r, tq_c, td_r, td_c, lse, delta, (__nv_bfloat16*)dqkv, S, nh, nkv, scale, nblk);
-  attn_bwd_kernel<false><<<dim3(B * nh, nblk, 1), 256, bwd::SMEM_BYTES, s>>>(
+  attn_bwd_kernel<false><<<dim3(B * nh, nblk, 1), bwd::THREADS, bwd::SMEM_BYTES, s>>>(
       tq_r, tq_c, td_r, td_c, lse, delta, (__nv_bfloat16*)dqkv, S, nh, nkv, scale, nblk);
   note_launch(3);
   DTG_LAUNCH_CHECK();

@@ -8,9 +8,11 @@
 //                              the next block's scores are computed during this block's softmax)
 //                              O     += P_j V_j  (P from shared memory, V as an MN-major operand)
 //   warp 2    TMEM allocator   512 columns: S0 | S1 | O
-//   warps 4-7 softmax          thread t owns query row t: tcgen05.ld of its score row, online
-//                              max/sum in fp32 with exp2, P -> bf16 -> 128B-swizzled shared memory,
-//                              O rescaled in TMEM only when some row's running max moved,
+//   warps 4-11 softmax         two threads per query row (64 score columns each; two warps per SM
+//                              sub-partition hide each other's latency): tcgen05.ld of the half row,
+//                              online max (halves combined through shared memory + a 64-thread named
+//                              barrier) / sum in fp32 with ex2.approx, P -> bf16 -> 128B-swizzled shared
+//                              memory, O rescaled in TMEM only when some row's running max moved,
 //                              final O / l and the logsumexp written from registers.
 //
 // Replaces torch SDPA / flash-attn-2 (mma.sync) that the reference uses.
@@ -31,11 +33,14 @@ constexpr int TILE_BYTES = 128 * 128 * 2;  // 32 KB: two 64-column halves of [12
 constexpr int HALF_BYTES = TILE_BYTES / 2;
 constexpr int OFF_Q = 0, OFF_K = TILE_BYTES, OFF_V = 3 * TILE_BYTES, OFF_P = 5 * TILE_BYTES;
 constexpr int OFF_BAR = 6 * TILE_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+constexpr int OFF_RED = OFF_BAR + 256;          // float [3][2][128]: row max exchange (double-buffered by block
+                                                // parity: a fast warp may already publish block j+1) + row sums
+constexpr int SMEM_BYTES = OFF_RED + 3072 + 1024;
+constexpr int THREADS = 384;
 constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O = 256;
 }  // namespace fwd
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(fwd::THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ o, float* __restrict__ lse,
                 int S, int nh, int nkv, float scale_log2, int num_m_blocks) {
   using namespace fwd;
@@ -72,9 +77,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
       mbar_init(&k_empty[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);
+      mbar_init(&s_empty[i], 8);
     }
-    mbar_init(p_full, 4);
+    mbar_init(p_full, 8);
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
@@ -154,20 +159,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
     }
   } else if (warp >= 4) {
     // ===================== softmax / correction / epilogue =====================
-    const int q = warp - 4;
-    const int row = q * 32 + lane;  // query row within the tile == TMEM lane
+    const int q = warp & 3;             // TMEM lane quarter this warp may touch
+    const int half = (warp - 4) >> 2;   // which 64 score columns (and which 64 output columns) are mine
+    const int row = q * 32 + lane;      // query row within the tile == TMEM lane
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    float m_run = -INFINITY, l_run = 0.f;
-    uint8_t* sp = smem + OFF_P;
+    float* red = reinterpret_cast<float*>(smem + OFF_RED);
+    float m_run = -INFINITY, l_run = 0.f;  // l_run: partial row sum over my columns
+    uint8_t* sp = smem + OFF_P + half * HALF_BYTES + row * 128;
     for (int j = 0; j < n_blocks; ++j) {
       const int st = j & 1;
       mbar_wait(&s_full[st], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
-      float s[128];
+      float s[64];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
-        tmem_ld_32x32b_x32(lane_addr + (st ? TM_S1 : TM_S0) + c * 32, r);
+        tmem_ld_32x32b_x32(lane_addr + (st ? TM_S1 : TM_S0) + half * 64 + c * 32, r);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(r[i]);
@@ -177,41 +184,46 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
       if (lane == 0) mbar_arrive(&s_empty[st]);  // scores are in registers now
       if (j == n_blocks - 1) {                   // diagonal block: mask keys after the query
 #pragma unroll
-        for (int i = 0; i < 128; ++i)
-          if (i > row) s[i] = -INFINITY;
+        for (int i = 0; i < 64; ++i)
+          if (half * 64 + i > row) s[i] = -INFINITY;
       }
-      float mx = m_run;
+      float mx = s[0];
 #pragma unroll
-      for (int i = 0; i < 128; ++i) mx = fmaxf(mx, s[i]);
-      const float alpha = exp2f((m_run - mx) * scale_log2);  // 0 on the first block (m_run = -inf)
+      for (int i = 1; i < 64; ++i) mx = fmaxf(mx, s[i]);
+      float* redj = red + (j & 1) * 256;
+      redj[half * 128 + row] = mx;
+      named_bar_sync(1 + q, 64);  // the two warps that share these 32 rows
+      mx = fmaxf(m_run, fmaxf(mx, redj[(half ^ 1) * 128 + row]));
+      const float alpha = fast_exp2((m_run - mx) * scale_log2);  // 0 on the first block (m_run = -inf)
       const float mb = mx * scale_log2;
       float sum = 0.f;
-      // P_{j} may only overwrite the shared buffer / O may only be touched once PV_{j-1} is done
-      if (j > 0) mbar_wait(pv_done, (uint32_t)((j - 1) & 1));
+      uint32_t pk[32];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {  // 16 chunks of 8 keys
-        float p[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          p[i] = exp2f(s[c * 8 + i] * scale_log2 - mb);
-          sum += p[i];
-        }
-        const bf16x8 pk = pack8(p);
-        const int half = c >> 3, cc = c & 7;
-        *reinterpret_cast<bf16x8*>(sp + half * HALF_BYTES + row * 128 + ((cc ^ (row & 7)) << 4)) = pk;
+      for (int i = 0; i < 64; i += 2) {
+        const float p0 = fast_exp2(fmaf(s[i], scale_log2, -mb));
+        const float p1 = fast_exp2(fmaf(s[i + 1], scale_log2, -mb));
+        sum += p0 + p1;
+        __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
       }
       l_run = l_run * alpha + sum;
       m_run = mx;
+      // P_j may only overwrite the shared buffer / O may only be touched once PV_{j-1} is done
+      if (j > 0) mbar_wait(pv_done, (uint32_t)((j - 1) & 1));
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(sp + ((c ^ (row & 7)) << 4)) =
+            make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
       if (j > 0 && __any_sync(0xffffffffu, alpha < 1.f)) {
         tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           uint32_t r[32];
-          tmem_ld_32x32b_x32(lane_addr + TM_O + c * 32, r);
+          tmem_ld_32x32b_x32(lane_addr + TM_O + half * 64 + c * 32, r);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-          tmem_st_32x32b_x32(lane_addr + TM_O + c * 32, r);
+          tmem_st_32x32b_x32(lane_addr + TM_O + half * 64 + c * 32, r);
         }
         tmem_st_wait();
       }
@@ -221,15 +233,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
       if (lane == 0) mbar_arrive(p_full);
     }
     // epilogue: O / l -> bf16 -> global ; logsumexp
+    red[512 + half * 128 + row] = l_run;
+    named_bar_sync(1 + q, 64);
+    const float l_tot = l_run + red[512 + (half ^ 1) * 128 + row];
     mbar_wait(pv_done, (uint32_t)((n_blocks - 1) & 1));
     tc_fence_after();
-    const float inv_l = 1.f / l_run;
+    const float inv_l = 1.f / l_tot;
     const long long tok = (long long)batch * S + q0 + row;
-    __nv_bfloat16* orow = o + (tok * nh + head) * (long long)D;
+    __nv_bfloat16* orow = o + (tok * nh + head) * (long long)D + half * 64;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       uint32_t r[32];
-      tmem_ld_32x32b_x32(lane_addr + TM_O + c * 32, r);
+      tmem_ld_32x32b_x32(lane_addr + TM_O + half * 64 + c * 32, r);
       tmem_ld_wait();
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
@@ -240,7 +255,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
       }
     }
     // natural-log logsumexp of the scaled scores
-    lse[((long long)batch * nh + head) * S + q0 + row] = m_run * scale_log2 * 0.6931471805599453f + __logf(l_run);
+    if (half == 0)
+      lse[((long long)batch * nh + head) * S + q0 + row] = m_run * scale_log2 * 0.6931471805599453f + __logf(l_tot);
   }
 
   tc_fence_before();
@@ -266,7 +282,7 @@ void attn_fwd(const void* qkv, void* o, float* lse, int B, int S, int nh, int nk
     attr = true;
   }
   const int num_m = S / 128;
-  attn_fwd_kernel<<<dim3(B * nh, num_m, 1), 256, fwd::SMEM_BYTES, s>>>(tm, (__nv_bfloat16*)o, lse, S, nh, nkv,
+  attn_fwd_kernel<<<dim3(B * nh, num_m, 1), fwd::THREADS, fwd::SMEM_BYTES, s>>>(tm, (__nv_bfloat16*)o, lse, S, nh, nkv,
                                                                       scale * 1.4426950408889634f, num_m);
   note_launch();
   DTG_LAUNCH_CHECK();

@@ -181,4 +181,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("adamw_flat", &adamw_flat);
   dtg::bind_comm(m);
   dtg::bind_attention(m);
+  dtg::bind_tp(m);
 }

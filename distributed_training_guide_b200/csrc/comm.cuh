@@ -8,7 +8,6 @@
 
 namespace dtg {
 
-constexpr int kMaxRanks = 8;
 constexpr int kMaxChannels = 256;  // one signal-pad channel per CTA of a collective kernel
 constexpr int kCommThreads = 512;
 constexpr long long kSpinTimeoutCycles = 20LL * 1000 * 1000 * 1000;  // ~10 s at 2 GHz
@@ -34,5 +33,18 @@ void comm_allgather(const SymmPtrs& shards, void* full, const SymmPads& pads, si
 void comm_reduce_scatter(const SymmPtrs& grads, void* out, const SymmPads& pads, size_t elem_off, size_t n, float scale,
                          int rank, int nranks, uint32_t epoch, int* err, int blocks, cudaStream_t s);
 void comm_barrier(const SymmPads& pads, int rank, int nranks, uint32_t epoch, int* err, cudaStream_t s);
+
+
+// ---- fused_tp.cu / cross_entropy.cu helpers used by the tensor-parallel path ------------------------
+void tp_reduce_parts(const void* parts, const void* residual, void* out, long long n, int nparts, cudaStream_t s);
+void vp_ce_stats(const void* logits, const long long* targets, void* stats, int T, int Vl, int v0, cudaStream_t s);
+void vp_ce_grad(void* logits, const long long* targets, const SymmPtrs& stats, float* row_loss, const float* n_valid,
+                int T, int Vl, int v0, int nranks, cudaStream_t s);
+void tp_embed_fwd(const long long* ids, const void* w, const SymmPtrs& dst, long long T, int rpp, int H, int Hl, int rank,
+                  cudaStream_t s);
+void tp_embed_bwd(const long long* ids, const SymmPtrs& dx, void* dw, long long T, int rpp, int H, int Hl, int rank,
+                  cudaStream_t s);
+void ce_count_valid(const long long* targets, float* n_valid, int T, cudaStream_t s);
+void ce_finalize(const float* row_loss, const float* n_valid, float* loss, int T, cudaStream_t s);
 
 }  // namespace dtg

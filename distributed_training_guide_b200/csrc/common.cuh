@@ -9,6 +9,8 @@
 
 namespace dtg {
 
+constexpr int kMaxRanks = 8;  // one NVSwitch domain
+
 // Every kernel launch of this extension is counted (bench.py reports it as `gpu_launches`).
 void note_launch(int n = 1);
 unsigned long long launch_count();

@@ -78,6 +78,17 @@ __global__ void ce_finalize_kernel(const float* __restrict__ row_loss, const flo
   if (threadIdx.x == 0) *loss = (*n_valid > 0.f) ? s / *n_valid : 0.f;
 }
 
+void ce_count_valid(const long long* targets, float* n_valid, int T, cudaStream_t s) {
+  count_valid_kernel<<<1, 1024, 0, s>>>(targets, n_valid, T);
+  note_launch();
+  DTG_LAUNCH_CHECK();
+}
+void ce_finalize(const float* row_loss, const float* n_valid, float* loss, int T, cudaStream_t s) {
+  ce_finalize_kernel<<<1, 1024, 0, s>>>(row_loss, n_valid, loss, T);
+  note_launch();
+  DTG_LAUNCH_CHECK();
+}
+
 void cross_entropy_fwd_bwd(void* logits, const long long* targets, float* row_loss, float* n_valid, float* loss,
                            int T, int V, cudaStream_t s) {
   if (V % 8 != 0) throw std::runtime_error("cross_entropy: vocab size must be a multiple of 8");

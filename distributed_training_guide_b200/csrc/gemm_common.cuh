@@ -1,10 +1,13 @@
 // Tile configuration shared by the tcgen05 GEMM and the fused GEMM+collective kernels.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cstdint>
 
+#include "common.cuh"
+
 #ifndef DTG_DEFAULT_GEMM_VARIANT
-#define DTG_DEFAULT_GEMM_VARIANT 1
+#define DTG_DEFAULT_GEMM_VARIANT 3
 #endif
 
 namespace dtg {
@@ -22,6 +25,26 @@ struct GemmCfg {
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
 };
+
+template <int N>
+struct TmapSet {
+  CUtensorMap m[N];
+};
+
+// Geometry of a tensor-parallel GEMM (all zero / unused for the plain GEMM)
+struct GemmDist {
+  int rows_per_peer;                 // rows (M- or K-direction) each rank contributes / owns
+  int m_tile_shift;                  // rotate the M tile order so every rank starts on its own rows
+  int k_shift;                       // rotate the K block order likewise
+  __nv_bfloat16* c_ptr[kMaxRanks];   // C_MODE 1: destination base (already offset to my slot) per owner
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ int tile_m(int t, int num_m_tiles, const GemmDist& d) {
+  int m = t % num_m_tiles + d.m_tile_shift;
+  return m >= num_m_tiles ? m - num_m_tiles : m;
+}
+#endif
 
 // TMA descriptor builders (gemm_tcgen05.cu)
 CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,

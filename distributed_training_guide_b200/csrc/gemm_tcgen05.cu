@@ -29,9 +29,17 @@ namespace dtg {
 
 using namespace ptx;
 
-template <bool A_K, bool B_K, int CG>
+// Distributed operand modes (tensor parallelism, fused_tp.cu):
+//   A_MODE / B_MODE  0 = one tensor map;  1 = rows (M) of A gathered from the ranks' symmetric buffers
+//                    (all-gather -> GEMM);  2 = the reduction dimension K gathered from the ranks (wgrad
+//                    over a sequence-sharded activation).  Tiles are fetched from the owning peer by TMA
+//                    over NVLink, so the transfer streams under the MMA pipeline.
+//   C_MODE           0 = local C;  1 = each `rows_per_peer` row chunk of C is stored into its owner's
+//                    staging buffer (GEMM -> reduce-scatter push).
+template <bool A_K, bool B_K, int CG, int A_MODE = 0, int B_MODE = 0, int C_MODE = 0>
 __global__ void __launch_bounds__(256, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+gemm_bf16_kernel(const __grid_constant__ TmapSet<(A_MODE ? kMaxRanks : 1)> tmAs,
+                 const __grid_constant__ TmapSet<(B_MODE ? kMaxRanks : 1)> tmBs, const __grid_constant__ GemmDist dist,
                  __nv_bfloat16* __restrict__ C, int M, int N, int K, long long ldc, int accumulate, int num_m_tiles,
                  int num_tiles) {
   using Cfg = GemmCfg<CG>;
@@ -53,8 +61,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int num_kb = (K + Cfg::BK - 1) / Cfg::BK;
 
   if (warp == 0 && elect_one()) {
-    prefetch_tensormap(&tmA);
-    prefetch_tensormap(&tmB);
+    prefetch_tensormap(&tmAs.m[0]);
+    prefetch_tensormap(&tmBs.m[0]);
   }
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < Cfg::STAGES; ++i) {
@@ -82,42 +90,65 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        const int m0 = (t % num_m_tiles) * (Cfg::BM * CG) + (int)cta_rank * Cfg::BM;
+        const int m0 = tile_m(t, num_m_tiles, dist) * (Cfg::BM * CG) + (int)cta_rank * Cfg::BM;
         const int nb = (t / num_m_tiles) * Cfg::BN + (int)cta_rank * Cfg::B_ROWS;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const CUtensorMap* tmA_p = &tmAs.m[0];
+        int a_m0 = m0;
+        if constexpr (A_MODE == 1) {  // this row block lives on rank m0 / rows_per_peer
+          const int peer = m0 / dist.rows_per_peer;
+          tmA_p = &tmAs.m[peer];
+          a_m0 = m0 - peer * dist.rows_per_peer;
+        }
+        for (int kbi = 0; kbi < num_kb; ++kbi) {
+          // K-gathered operands start with the local rank's slice of K
+          const int kb = (A_MODE == 2 || B_MODE == 2) ? (kbi + dist.k_shift) % num_kb : kbi;
           const int k0 = kb * Cfg::BK;
+          int a_k0 = k0, b_k0 = k0;
+          const CUtensorMap* tmB_p = &tmBs.m[0];
+          if constexpr (A_MODE == 2) {
+            const int peer = k0 / dist.rows_per_peer;
+            tmA_p = &tmAs.m[peer];
+            a_k0 = k0 - peer * dist.rows_per_peer;
+          }
+          if constexpr (B_MODE == 2) {
+            const int peer = k0 / dist.rows_per_peer;
+            tmB_p = &tmBs.m[peer];
+            b_k0 = k0 - peer * dist.rows_per_peer;
+          }
+          const CUtensorMap& tmA = *tmA_p;
+          const CUtensorMap& tmB = *tmB_p;
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           if constexpr (CG == 1) {
             mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
             if constexpr (A_K) {
-              tma_load_2d(&tmA, &full[stage], sa, k0, m0);
+              tma_load_2d(&tmA, &full[stage], sa, a_k0, a_m0);
             } else {
 #pragma unroll
-              for (int j = 0; j < Cfg::BM / 64; ++j) tma_load_2d(&tmA, &full[stage], sa + j * 8192, m0 + 64 * j, k0);
+              for (int j = 0; j < Cfg::BM / 64; ++j) tma_load_2d(&tmA, &full[stage], sa + j * 8192, a_m0 + 64 * j, a_k0);
             }
             if constexpr (B_K) {
-              tma_load_2d(&tmB, &full[stage], sb, k0, nb);
+              tma_load_2d(&tmB, &full[stage], sb, b_k0, nb);
             } else {
 #pragma unroll
-              for (int j = 0; j < Cfg::B_ROWS / 64; ++j) tma_load_2d(&tmB, &full[stage], sb + j * 8192, nb + 64 * j, k0);
+              for (int j = 0; j < Cfg::B_ROWS / 64; ++j) tma_load_2d(&tmB, &full[stage], sb + j * 8192, nb + 64 * j, b_k0);
             }
           } else {
             const uint32_t bar = mapa(smem_u32(&full[stage]), 0);  // the leader CTA's barrier
             if (is_leader) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
             else mbar_arrive_cluster(bar);
             if constexpr (A_K) {
-              tma_load_2d_cg2(&tmA, bar, sa, k0, m0);
+              tma_load_2d_cg2(&tmA, bar, sa, a_k0, a_m0);
             } else {
 #pragma unroll
-              for (int j = 0; j < Cfg::BM / 64; ++j) tma_load_2d_cg2(&tmA, bar, sa + j * 8192, m0 + 64 * j, k0);
+              for (int j = 0; j < Cfg::BM / 64; ++j) tma_load_2d_cg2(&tmA, bar, sa + j * 8192, a_m0 + 64 * j, a_k0);
             }
             if constexpr (B_K) {
-              tma_load_2d_cg2(&tmB, bar, sb, k0, nb);
+              tma_load_2d_cg2(&tmB, bar, sb, b_k0, nb);
             } else {
 #pragma unroll
-              for (int j = 0; j < Cfg::B_ROWS / 64; ++j) tma_load_2d_cg2(&tmB, bar, sb + j * 8192, nb + 64 * j, k0);
+              for (int j = 0; j < Cfg::B_ROWS / 64; ++j) tma_load_2d_cg2(&tmB, bar, sb + j * 8192, nb + 64 * j, b_k0);
             }
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -160,13 +191,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-      const int m0 = (t % num_m_tiles) * (Cfg::BM * CG) + (int)cta_rank * Cfg::BM;
+      const int m0 = tile_m(t, num_m_tiles, dist) * (Cfg::BM * CG) + (int)cta_rank * Cfg::BM;
       const int n0 = (t / num_m_tiles) * Cfg::BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::BN);
       __nv_bfloat16* crow = C + (size_t)row * ldc + n0;
+      if constexpr (C_MODE == 1) {  // push this row into the staging buffer of the rank that owns it
+        const int owner = row / dist.rows_per_peer;
+        crow = dist.c_ptr[owner < kMaxRanks ? owner : 0] + (size_t)(row - owner * dist.rows_per_peer) * ldc + n0;
+      }
 #pragma unroll 1
       for (int c = 0; c < Cfg::BN; c += 32) {
         uint32_t r[32];
@@ -273,17 +308,31 @@ int default_gemm_variant() {
   return env;
 }
 
-template <bool A_K, bool B_K, int CG>
-static void launch_gemm(const void* A, const void* B, void* C, int M, int N, int K, long long lda, long long ldb,
-                        long long ldc, bool accumulate, cudaStream_t s) {
+// One launcher for the plain and the tensor-parallel GEMMs.  `a_srcs` / `b_srcs`: base pointer of the
+// operand on every rank (only [0] is used in mode 0); `dist.c_ptr` set by the caller for C_MODE 1.
+template <bool A_K, bool B_K, int CG, int A_MODE, int B_MODE, int C_MODE>
+static void launch_gemm(const void* const* a_srcs, const void* const* b_srcs, void* C, int M, int N, int K,
+                        long long lda, long long ldb, long long ldc, bool accumulate, GemmDist dist, int nranks,
+                        cudaStream_t s) {
   using Cfg = GemmCfg<CG>;
-  const CUtensorMap tmA = A_K ? make_tmap_2d(A, K, M, lda * 2, 64, Cfg::BM) : make_tmap_2d(A, M, K, lda * 2, 64, 64);
-  const CUtensorMap tmB =
-      B_K ? make_tmap_2d(B, K, N, ldb * 2, 64, Cfg::B_ROWS) : make_tmap_2d(B, N, K, ldb * 2, 64, 64);
+  TmapSet<(A_MODE ? kMaxRanks : 1)> tmA;
+  TmapSet<(B_MODE ? kMaxRanks : 1)> tmB;
+  const int rpp = dist.rows_per_peer;
+  for (int p = 0; p < (A_MODE ? nranks : 1); ++p) {
+    const int rows = (A_MODE == 1) ? rpp : M;   // M extent of this source
+    const int ks = (A_MODE == 2) ? rpp : K;     // K extent of this source
+    tmA.m[p] = A_K ? make_tmap_2d(a_srcs[p], ks, rows, lda * 2, 64, Cfg::BM) : make_tmap_2d(a_srcs[p], rows, ks, lda * 2, 64, 64);
+  }
+  for (int p = 0; p < (B_MODE ? nranks : 1); ++p) {
+    const int ks = (B_MODE == 2) ? rpp : K;
+    tmB.m[p] = B_K ? make_tmap_2d(b_srcs[p], ks, N, ldb * 2, 64, Cfg::B_ROWS) : make_tmap_2d(b_srcs[p], N, ks, ldb * 2, 64, 64);
+  }
+  for (int p = (A_MODE ? nranks : 1); p < (A_MODE ? kMaxRanks : 1); ++p) tmA.m[p] = tmA.m[0];
+  for (int p = (B_MODE ? nranks : 1); p < (B_MODE ? kMaxRanks : 1); ++p) tmB.m[p] = tmB.m[0];
   const int num_m_tiles = (M + Cfg::BM * CG - 1) / (Cfg::BM * CG);
   const int num_n_tiles = (N + Cfg::BN - 1) / Cfg::BN;
   const int num_tiles = num_m_tiles * num_n_tiles;
-  auto kern = gemm_bf16_kernel<A_K, B_K, CG>;
+  auto kern = gemm_bf16_kernel<A_K, B_K, CG, A_MODE, B_MODE, C_MODE>;
   static bool attr_set = false;
   if (!attr_set) {
     DTG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -303,7 +352,7 @@ static void launch_gemm(const void* A, const void* B, void* C, int M, int N, int
   attrs[0].val.clusterDim.z = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
-  DTG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, (__nv_bfloat16*)C, M, N, K, ldc, accumulate ? 1 : 0,
+  DTG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, dist, (__nv_bfloat16*)C, M, N, K, ldc, accumulate ? 1 : 0,
                                     num_m_tiles, num_tiles));
   note_launch();
 }
@@ -321,13 +370,13 @@ int gemm_max_active_clusters(int cg) {
   cfg.numAttrs = 1;
   int n = -1;
   if (cg == 2) {
-    auto kern = gemm_bf16_kernel<true, true, 2>;
+    auto kern = gemm_bf16_kernel<true, true, 2, 0, 0, 0>;
     cfg.gridDim = dim3(148);
     cfg.dynamicSmemBytes = GemmCfg<2>::SMEM_BYTES;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2>::SMEM_BYTES);
     cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
   } else {
-    auto kern = gemm_bf16_kernel<true, true, 1>;
+    auto kern = gemm_bf16_kernel<true, true, 1, 0, 0, 0>;
     cfg.gridDim = dim3(148);
     cfg.dynamicSmemBytes = GemmCfg<1>::SMEM_BYTES;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::SMEM_BYTES);
@@ -342,18 +391,67 @@ void gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, long 
   if ((N % 8) || (ldc % 8) || (lda % 8) || (ldb % 8))
     throw std::runtime_error("gemm_bf16: N and the leading dimensions must be multiples of 8 elements");
   if (variant == 0) variant = default_gemm_variant();
+  if (variant == 3) variant = (M > 128) ? 2 : 1;  // auto: the CTA-pair tile is 256 rows tall
   const int cg = (variant == 2) ? 2 : 1;
-#define DTG_GEMM_CASE(AK, BK)                                                                         \
-  if (a_kmajor == AK && b_kmajor == BK) {                                                             \
-    if (cg == 2) launch_gemm<AK, BK, 2>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, s);               \
-    else launch_gemm<AK, BK, 1>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, s);                       \
-    return;                                                                                           \
+  const void* as[1] = {A};
+  const void* bs[1] = {B};
+  GemmDist dist{};
+#define DTG_GEMM_CASE(AK, BK)                                                                                    \
+  if (a_kmajor == AK && b_kmajor == BK) {                                                                        \
+    if (cg == 2) launch_gemm<AK, BK, 2, 0, 0, 0>(as, bs, C, M, N, K, lda, ldb, ldc, accumulate, dist, 1, s);      \
+    else launch_gemm<AK, BK, 1, 0, 0, 0>(as, bs, C, M, N, K, lda, ldb, ldc, accumulate, dist, 1, s);              \
+    return;                                                                                                      \
   }
   DTG_GEMM_CASE(true, true)
   DTG_GEMM_CASE(true, false)
   DTG_GEMM_CASE(false, false)
   DTG_GEMM_CASE(false, true)
 #undef DTG_GEMM_CASE
+}
+
+// Tensor-parallel GEMMs over NVLink symmetric buffers (always the CTA-pair kernel).
+//   mode 1  all-gather(M) -> GEMM : A = concat_p a_srcs[p] ([rows_per_peer, K] each, K-major)
+//   mode 2  GEMM -> reduce-scatter push : row chunk c of C goes to c_dsts[c] (already offset to my slot)
+//   mode 3  wgrad with B gathered along K : B = concat_p b_srcs[p] ([rows_per_peer, N] each), A MN-major local
+//   mode 4  wgrad with A gathered along K : A = concat_p a_srcs[p] ([rows_per_peer, M] each), B MN-major local
+void gemm_bf16_dist(int mode, const void* const* a_srcs, const void* const* b_srcs, void* const* c_dsts, int M, int N,
+                    int K, long long lda, long long ldb, long long ldc, bool b_kmajor, bool accumulate, int nranks,
+                    int rank, int rows_per_peer, cudaStream_t s) {
+  if ((N % 8) || (ldc % 8) || (lda % 8) || (ldb % 8))
+    throw std::runtime_error("gemm_bf16_dist: N and the leading dimensions must be multiples of 8 elements");
+  if (nranks < 1 || nranks > kMaxRanks) throw std::runtime_error("gemm_bf16_dist: 1..8 ranks");
+  GemmDist dist{};
+  dist.rows_per_peer = rows_per_peer;
+  constexpr int TM = GemmCfg<2>::BM * 2;
+  if (mode == 1 || mode == 2) {
+    if (rows_per_peer % TM != 0 || rows_per_peer * nranks != M)
+      throw std::runtime_error("gemm_bf16_dist: rows per rank must be a multiple of 256 and sum to M");
+    dist.m_tile_shift = (mode == 1) ? rank * (rows_per_peer / TM) : ((rank + 1) % nranks) * (rows_per_peer / TM);
+  } else {
+    if (rows_per_peer % 64 != 0 || rows_per_peer * nranks != K)
+      throw std::runtime_error("gemm_bf16_dist: K rows per rank must be a multiple of 64 and sum to K");
+    dist.k_shift = rank * (rows_per_peer / 64);
+  }
+  for (int p = 0; p < nranks && c_dsts; ++p) dist.c_ptr[p] = (__nv_bfloat16*)c_dsts[p];
+  void* C = c_dsts ? c_dsts[0] : nullptr;
+  switch (mode) {
+    case 1:
+      if (b_kmajor) launch_gemm<true, true, 2, 1, 0, 0>(a_srcs, b_srcs, C, M, N, K, lda, ldb, ldc, accumulate, dist, nranks, s);
+      else launch_gemm<true, false, 2, 1, 0, 0>(a_srcs, b_srcs, C, M, N, K, lda, ldb, ldc, accumulate, dist, nranks, s);
+      break;
+    case 2:
+      if (b_kmajor) launch_gemm<true, true, 2, 0, 0, 1>(a_srcs, b_srcs, C, M, N, K, lda, ldb, ldc, false, dist, nranks, s);
+      else launch_gemm<true, false, 2, 0, 0, 1>(a_srcs, b_srcs, C, M, N, K, lda, ldb, ldc, false, dist, nranks, s);
+      break;
+    case 3:
+      launch_gemm<false, false, 2, 0, 2, 0>(a_srcs, b_srcs, C, M, N, K, lda, ldb, ldc, accumulate, dist, nranks, s);
+      break;
+    case 4:
+      launch_gemm<false, false, 2, 2, 0, 0>(a_srcs, b_srcs, C, M, N, K, lda, ldb, ldc, accumulate, dist, nranks, s);
+      break;
+    default:
+      throw std::runtime_error("gemm_bf16_dist: unknown mode");
+  }
 }
 
 }  // namespace dtg

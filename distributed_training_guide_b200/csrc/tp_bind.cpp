@@ -1,0 +1,91 @@
+// Python bindings of the tensor-parallel kernels (distributed GEMM modes, partial-sum reduce,
+// vocab-parallel cross entropy, hidden-parallel embedding).
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <pybind11/stl.h>
+#include <torch/extension.h>
+
+#include "api.h"
+#include "comm.cuh"
+#include "comm_api.h"
+
+namespace dtg {
+namespace {
+using torch::Tensor;
+inline cudaStream_t stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+SymmPtrs plain(const std::vector<uint64_t>& ptrs) {
+  SymmPtrs s{};
+  TORCH_CHECK(ptrs.size() >= 1 && ptrs.size() <= (size_t)kMaxRanks, "1..8 ranks supported");
+  for (size_t k = 0; k < ptrs.size(); ++k) s.ptr[k] = (char*)ptrs[k];
+  return s;
+}
+
+void py_gemm_dist(int64_t mode, const std::vector<uint64_t>& a_ptrs, const std::vector<uint64_t>& b_ptrs,
+                  const std::vector<uint64_t>& c_ptrs, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                  int64_t ldc, bool b_kmajor, bool accumulate, int64_t nranks, int64_t rank, int64_t rows_per_peer) {
+  const void* as[kMaxRanks] = {nullptr};
+  const void* bs[kMaxRanks] = {nullptr};
+  void* cs[kMaxRanks] = {nullptr};
+  for (size_t i = 0; i < a_ptrs.size() && i < (size_t)kMaxRanks; ++i) as[i] = (const void*)a_ptrs[i];
+  for (size_t i = 0; i < b_ptrs.size() && i < (size_t)kMaxRanks; ++i) bs[i] = (const void*)b_ptrs[i];
+  for (size_t i = 0; i < c_ptrs.size() && i < (size_t)kMaxRanks; ++i) cs[i] = (void*)c_ptrs[i];
+  if (mode != 2) {  // local C: replicate so dist.c_ptr[0] is valid
+    for (int i = 1; i < kMaxRanks; ++i) cs[i] = cs[0];
+  }
+  dtg::gemm_bf16_dist((int)mode, as, bs, cs, (int)M, (int)N, (int)K, lda, ldb, ldc, b_kmajor, accumulate, (int)nranks,
+                      (int)rank, (int)rows_per_peer, stream());
+}
+
+void py_reduce_parts(const Tensor& parts, const c10::optional<Tensor>& residual, Tensor& out) {
+  TORCH_CHECK(parts.is_contiguous() && out.is_contiguous() && parts.scalar_type() == at::kBFloat16, "bad tensors");
+  const int64_t nparts = parts.size(0);
+  TORCH_CHECK(parts.numel() == nparts * out.numel(), "parts must be [nparts, *out.shape]");
+  const c10::cuda::CUDAGuard guard(out.device());
+  dtg::tp_reduce_parts(parts.data_ptr(), residual.has_value() ? residual->data_ptr() : nullptr, out.data_ptr(),
+                       out.numel(), (int)nparts, stream());
+}
+
+void py_vp_ce_stats(const Tensor& logits, const Tensor& targets, Tensor& stats, int64_t v0) {
+  TORCH_CHECK(logits.is_contiguous() && logits.scalar_type() == at::kBFloat16 && stats.scalar_type() == at::kFloat, "bad");
+  const c10::cuda::CUDAGuard guard(logits.device());
+  dtg::vp_ce_stats(logits.data_ptr(), (const long long*)targets.data_ptr<int64_t>(), stats.data_ptr(), (int)logits.size(0),
+                   (int)logits.size(1), (int)v0, stream());
+}
+
+Tensor py_vp_ce_grad(Tensor& logits, const Tensor& targets, const std::vector<uint64_t>& stats_ptrs, int64_t v0) {
+  const c10::cuda::CUDAGuard guard(logits.device());
+  const int T = (int)logits.size(0);
+  Tensor scratch = torch::empty({T + 2}, logits.options().dtype(at::kFloat));
+  float* sp = scratch.data_ptr<float>();
+  const long long* tg = (const long long*)targets.data_ptr<int64_t>();
+  dtg::ce_count_valid(tg, sp, T, stream());
+  dtg::vp_ce_grad(logits.data_ptr(), tg, plain(stats_ptrs), sp + 2, sp, T, (int)logits.size(1), (int)v0,
+                  (int)stats_ptrs.size(), stream());
+  dtg::ce_finalize(sp + 2, sp, sp + 1, T, stream());
+  return scratch.slice(0, 1, 2).reshape({});
+}
+
+void py_embed_fwd(const Tensor& ids, const Tensor& w, const std::vector<uint64_t>& dst_ptrs, int64_t rpp, int64_t H,
+                  int64_t rank) {
+  const c10::cuda::CUDAGuard guard(w.device());
+  dtg::tp_embed_fwd((const long long*)ids.data_ptr<int64_t>(), w.data_ptr(), plain(dst_ptrs), ids.numel(), (int)rpp,
+                    (int)H, (int)w.size(1), (int)rank, stream());
+}
+void py_embed_bwd(const Tensor& ids, const std::vector<uint64_t>& dx_ptrs, Tensor& dw, int64_t rpp, int64_t H,
+                  int64_t rank) {
+  const c10::cuda::CUDAGuard guard(dw.device());
+  dtg::tp_embed_bwd((const long long*)ids.data_ptr<int64_t>(), plain(dx_ptrs), dw.data_ptr(), ids.numel(), (int)rpp,
+                    (int)H, (int)dw.size(1), (int)rank, stream());
+}
+}  // namespace
+
+void bind_tp(pybind11::module_& m) {
+  m.def("gemm_dist", &py_gemm_dist);
+  m.def("tp_reduce_parts", &py_reduce_parts);
+  m.def("vp_ce_stats", &py_vp_ce_stats);
+  m.def("vp_ce_grad", &py_vp_ce_grad);
+  m.def("tp_embed_fwd", &py_embed_fwd);
+  m.def("tp_embed_bwd", &py_embed_bwd);
+}
+}  // namespace dtg

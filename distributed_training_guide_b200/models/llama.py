@@ -52,6 +52,23 @@ def init_parameter_(p, name: str, seed: int, std: float = 0.02, full_shape=None,
     p.copy_(full.to(p.dtype))
 
 
+#: which dimension of each parameter tensor parallelism splits (None = replicated)
+TP_SHARD_DIM = {"q_proj": 0, "k_proj": 0, "v_proj": 0, "gate_proj": 0, "up_proj": 0, "o_proj": 1, "down_proj": 1,
+                "embed_tokens": 1, "lm_head": 0}
+
+
+def tp_shard_spec(name: str, p, tp_size: int, tp_rank: int) -> dict:
+    """init_parameter_ kwargs that make rank ``tp_rank`` hold its slice of the full parameter."""
+    if tp_size == 1:
+        return {}
+    for key, dim in TP_SHARD_DIM.items():
+        if f"{key}.weight" in name:
+            full = list(p.shape)
+            full[dim] *= tp_size
+            return dict(full_shape=full, shard_dim=dim, shard_index=tp_rank, shard_count=tp_size)
+    return {}
+
+
 class Linear(nn.Module):
     """Bias-free projection holding ``weight`` [out, in] (HF naming)."""
 
@@ -190,8 +207,6 @@ class LlamaDecoderLayer(nn.Module):
         """x: [B,S,H] branch output of the previous layer (or the embeddings);
         residual: running residual stream *before* adding x (None for the first layer).
         Returns (mlp_out, residual) with the final add again deferred to the consumer."""
-        if self.tp is not None:
-            return self.tp.layer_forward(self, x, residual, cos, sin)
         att = self.self_attn
         B, S, _ = x.shape
         y, h = self.input_layernorm(x, residual)
@@ -209,7 +224,10 @@ class LlamaDecoderLayer(nn.Module):
 class LlamaModel(nn.Module):
     def __init__(self, config: ModelConfig, dtype=None, device=None, tp_size=1):
         super().__init__()
-        self.embed_tokens = Embedding(config.vocab_size, config.hidden_size, dtype, device)
+        assert config.hidden_size % tp_size == 0
+        # tensor parallel: the table is sharded over the hidden dimension (reference: ColwiseParallel on
+        # nn.Embedding, 06-tensor-parallel/train_llm.py:82)
+        self.embed_tokens = Embedding(config.vocab_size, config.hidden_size // tp_size, dtype, device)
         self.layers = nn.ModuleList(
             [LlamaDecoderLayer(config, i, dtype, device, tp_size) for i in range(config.num_hidden_layers)]
         )
@@ -222,8 +240,10 @@ class LlamaForCausalLM(nn.Module):
         super().__init__()
         self.config = config
         self.tp_size = tp_size
+        self.tp_rank = 0  # set by the tensor-parallel strategy before init_weights
         self.model = LlamaModel(config, dtype, device, tp_size)
-        vocab_local = config.vocab_size
+        assert config.vocab_size % tp_size == 0
+        vocab_local = config.vocab_size // tp_size  # vocabulary-sharded head (loss-parallel)
         self.lm_head = Linear(config.hidden_size, vocab_local, dtype, device)
         if config.tie_word_embeddings:
             self.lm_head.weight = self.model.embed_tokens.weight
@@ -244,7 +264,7 @@ class LlamaForCausalLM(nn.Module):
         self._init_seed = seed
         for name, p in self.named_parameters():
             if not p.is_meta:
-                init_parameter_(p, name, seed, std)
+                init_parameter_(p, name, seed, std, **tp_shard_spec(name, p, self.tp_size, getattr(self, "tp_rank", 0)))
 
     def num_parameters(self) -> int:
         return sum(p.numel() for p in self.parameters())

@@ -42,7 +42,8 @@ class SymmBuffer:
 
 
 class SymmGroup:
-    def __init__(self, device: torch.device, pg=None, ranks: Optional[List[int]] = None, comm_blocks: int = 32):
+    def __init__(self, device: torch.device, pg=None, ranks: Optional[List[int]] = None,
+                 comm_blocks: Optional[int] = None):
         self.C = _ext.load(required=True)
         self.device = torch.device(device)
         self.pg = pg
@@ -53,6 +54,14 @@ class SymmGroup:
             self.world, self.rank = 1, 0
         if self.world not in (1, 2, 4, 8):
             raise ValueError(f"symmetric collectives support 1/2/4/8 ranks, got {self.world}")
+        if comm_blocks is None:
+            # CTAs per collective kernel.  One rank: the fused kernel is a pure HBM-bound AdamW (14 B/element),
+            # it needs the whole chip to reach memory bandwidth.  Several ranks: enough CTAs to keep
+            # ~1 MB of 16-byte NVLink loads in flight (~2 us latency x ~800 GB/s) without starving the
+            # tensor-core kernels it overlaps with.
+            import os
+
+            comm_blocks = int(os.environ.get("DTG_COMM_BLOCKS", 256 if self.world == 1 else 96))
         self.comm_blocks = min(comm_blocks, int(self.C.SYMM_MAX_CHANNELS))
         self._peer_handles = []
         self.epoch = 0

@@ -68,7 +68,7 @@ class FSDPEngine:
     N_GRAD_SLOTS = 2
 
     def __init__(self, model, env, dtype, symm=None, pg=None, world_size=1, rank=0, seed=0, cpu_offload=False,
-                 prefetch=True, lr=3e-5):
+                 prefetch=True, lr=3e-5, init_fn=None, pre_reduce=None):
         self.model, self.env, self.dtype = model, env, dtype
         self.symm, self.pg, self.world, self.rank = symm, pg, world_size, rank
         self.device = env.device
@@ -76,6 +76,7 @@ class FSDPEngine:
         self.cpu_offload = cpu_offload
         self.prefetch = prefetch
         self.sync_enabled = True
+        self.pre_reduce = pre_reduce  # 2-D: sum the replicated (norm) gradients over the tp group first
         core = model.model
         self.layers = list(core.layers)
         L = len(self.layers)
@@ -126,7 +127,10 @@ class FSDPEngine:
             assert g.padded_numel == n_pad
             # deterministic init of the whole group inside the slot, then keep only my shard
             for n, p in named:
-                init_parameter_(p, n, seed)
+                if init_fn is not None:
+                    init_fn(p, n)  # tensor-parallel slices
+                else:
+                    init_parameter_(p, n, seed)
             per = g.padded_numel // world_size
             sh = symmetric(per)
             sh.copy_(g.param[rank * per:(rank + 1) * per])
@@ -314,6 +318,8 @@ class FSDPEngine:
         sh = self.shard_of[g.name]
         opt = self.optimizer
         st = opt.state[sh.param]
+        if self.pre_reduce is not None:
+            self.pre_reduce(g)
         if not self.use_kernels:
             if self.world > 1:
                 buf = g.grad.float()

@@ -284,3 +284,171 @@ class FullyShardedDataParallel(Strategy):
         if self.symm is not None:
             torch.cuda.synchronize()
             self.symm.check()
+
+
+class TwoDParallel(Strategy):
+    """Chapters 06 / 07: tensor parallel + sequence parallel inside a contiguous ``tp`` group
+    (``parallel/tp.py``: collectives fused into the tcgen05 GEMMs), and — when the data-parallel
+    size is > 1 — FSDP of the TP-local shards over the strided ``dp`` group (``parallel/fsdp.py``),
+    i.e. the 2-D mesh of ``07-2d-parallel/train_llm.py:47-53,121-123``.  The sampler is keyed on
+    the dp coordinate so TP peers read identical batches (``06-tensor-parallel/train_llm.py:141-147``)."""
+
+    chapter = "07-2d-parallel"
+
+    def __init__(self, args=None, tp_size=None):
+        super().__init__(args)
+        self.tp_size_arg = tp_size
+        self.engine = None
+        self.mesh = None
+        self.tp_symm = None
+        self.dp_symm = None
+
+    def _tp_size(self, args, world):
+        t = self.tp_size_arg or getattr(args, "tensor_parallel", None) or world
+        return min(int(t), world)
+
+    def setup(self, args):
+        from .mesh import build_mesh
+
+        env = super().setup(args)
+        self.tp_size = self._tp_size(args, env.world_size)
+        self.mesh = build_mesh(env.world_size, env.rank, self.tp_size, create_groups=env.distributed)
+        self.dp_size, self.dp_rank = self.mesh.dp_size, self.mesh.dp_rank
+        return env
+
+    def build_model(self, args, config):
+        from . import symm as symm_mod
+        from .fsdp import FSDPEngine
+        from .tp import TensorParallelRuntime, TPContext
+
+        env, mesh = self.env, self.mesh
+        cuda = env.device.type == "cuda"
+        seed = getattr(args, "seed", 0)
+        use_fsdp = mesh.dp_size > 1
+        with self.data_guard():
+            model = build_model(config, dtype=self.dtype(), device="meta" if use_fsdp else env.device,
+                                tp_size=mesh.tp_size, init=False)
+        model.tp_rank = mesh.tp_rank
+        if cuda:
+            if mesh.tp_size > 1:
+                self.tp_symm = symm_mod.SymmGroup(env.device, pg=mesh.tp_group)
+            else:
+                self.tp_symm = symm_mod.SymmGroup(env.device, ranks=[0])
+        max_tokens = args.batch_size * args.seq_length
+        ctx = TPContext(mesh.tp_size, mesh.tp_rank, mesh.tp_group, self.tp_symm, env.device, config.hidden_size,
+                        max_tokens, config.num_hidden_layers, self.dtype())
+        self.tp_ctx = ctx
+        if use_fsdp:
+            if cuda:
+                self.dp_symm = symm_mod.SymmGroup(env.device, pg=mesh.dp_group)
+            self.engine = FSDPEngine(model, env, self.dtype(), symm=self.dp_symm, pg=mesh.dp_group,
+                                     world_size=mesh.dp_size, rank=mesh.dp_rank, seed=seed,
+                                     cpu_offload=getattr(args, "cpu_offload", False),
+                                     init_fn=lambda p, n: _tp_init(model, p, n, seed), pre_reduce=self._sync_replicated)
+            self.groups = self.engine.groups
+        else:
+            model.init_weights(seed=seed)
+            self.registry = {}
+            alloc = self.tp_symm.allocator(self.registry) if cuda else None
+            self.groups = build_groups(model, env.device, self.dtype(), world_size=mesh.tp_size, alloc=alloc)
+        model.tp = TensorParallelRuntime(ctx)
+        model.activation_checkpointing = bool(getattr(args, "checkpoint_activations", False))
+        self.model = model
+        return model
+
+    def num_parameters(self, model):
+        return model.config.num_parameters()
+
+    # replicated parameters (norm gains) see only this rank's sequence shard: sum their grads over tp
+    def _norm_regions(self, g):
+        out = []
+        for n, p, o in zip(g.names, g.params, g.offsets):
+            if n.endswith("norm.weight") or n.endswith("layernorm.weight"):
+                out.append((o, p.numel()))
+        return out
+
+    def _sync_replicated(self, g):
+        ctx = self.tp_ctx
+        if ctx.t == 1:
+            return
+        for off, n in self._norm_regions(g):
+            view = g.grad[off:off + n]
+            if ctx.use_kernels:
+                if not hasattr(self, "_norm_scratch"):
+                    self._norm_scratch = self.tp_symm.alloc(max(n, 8 * ctx.t * 16), self.dtype())
+                sc = self._norm_scratch
+                sc.local[:n].copy_(view)
+                self.tp_symm.allreduce_scale_(sc, 0, _round_up_to(n, 8 * ctx.t), 1.0, blocks=4)
+                view.copy_(sc.local[:n])
+            else:
+                ctx.all_reduce_(view)
+
+    def build_optimizer(self, args, model, lr):
+        if self.engine is not None:
+            return self.engine.build_optimizer(lr)
+        return FlatAdamW(self.groups, lr=lr)
+
+    def pre_step(self, model):
+        if self.engine is not None:
+            self.engine.pre_step()
+
+    def backward(self, model, loss):
+        loss.backward()
+        if self.engine is None:  # pure TP: fix up the replicated gradients before the optimizer runs
+            for g in self.groups:
+                self._sync_replicated(g)
+
+    def save_checkpoint(self, exp_dir, model, optimizer, lr_scheduler, state):
+        env = self.env
+        ws = env.world_size if env.distributed else 1
+        if env.device.type == "cuda":
+            torch.cuda.synchronize()
+        ckpt_utils.save_sharded(exp_dir, self._sharded_state(optimizer), lr_scheduler, state, env.rank, ws)
+        self.barrier()
+
+    def load_checkpoint(self, exp_dir, model, optimizer, lr_scheduler):
+        env = self.env
+        ws = env.world_size if env.distributed else 1
+        return ckpt_utils.load_sharded(exp_dir, self._sharded_state(optimizer), lr_scheduler, env.device, env.rank, ws)
+
+    def _sharded_state(self, optimizer):
+        if self.engine is not None:
+            return self.engine.sharded_state()
+        model_sd = {g.name: g.param for g in self.groups}
+        opt_sd = {}
+        for g in self.groups:
+            st = optimizer.state[g.param]
+            opt_sd[f"{g.name}.exp_avg"], opt_sd[f"{g.name}.exp_avg_sq"] = st["exp_avg"], st["exp_avg_sq"]
+        return {"model": model_sd, "optimizer": opt_sd}
+
+    def teardown(self):
+        for sg in (self.tp_symm, self.dp_symm):
+            if sg is not None:
+                torch.cuda.synchronize()
+                sg.check()
+
+
+def _round_up_to(x, m):
+    return (x + m - 1) // m * m
+
+
+def _tp_init(model, p, name, seed):
+    from ..models.llama import init_parameter_, tp_shard_spec
+
+    init_parameter_(p, name, seed, **tp_shard_spec(name, p, model.tp_size, model.tp_rank))
+
+
+class TensorParallel(TwoDParallel):
+    """Chapter 06: tensor parallel over all GPUs of the node (``tp = gpus on node``), data parallel
+    across nodes — the mesh of ``06-tensor-parallel/train_llm.py:37-55``.  (Unlike the reference, the
+    data-parallel replicas ARE kept in sync: with dp > 1 this is the 2-D engine, SURVEY.md §8 #7.)"""
+
+    chapter = "06-tensor-parallel"
+
+    def _tp_size(self, args, world):
+        if self.tp_size_arg:
+            return min(self.tp_size_arg, world)
+        import os
+
+        local = int(os.environ.get("LOCAL_WORLD_SIZE", "0")) or (torch.cuda.device_count() if torch.cuda.is_available() else world)
+        return max(1, min(local, world))

@@ -1,0 +1,132 @@
+"""Tensor-parallel fused kernels (AG->GEMM, GEMM->RS, K-gathered wgrad, vocab-parallel CE, hidden-parallel
+embedding) on 2 GPUs vs a single-GPU run with the same seed and batch."""
+import pytest
+import torch
+
+from dist_utils import run_distributed
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+
+
+def _gemm_modes(rank, world):
+    """Each distributed GEMM mode against torch.distributed + matmul."""
+    import torch.distributed as dist
+
+    from distributed_training_guide_b200 import _ext
+    from distributed_training_guide_b200.parallel import bootstrap
+    from distributed_training_guide_b200.parallel.symm import SymmGroup
+
+    env = bootstrap.init_distributed("cuda")
+    dev, C = env.device, _ext.load(True)
+    sg = SymmGroup(dev)
+    t = world
+    Tl, H, n = 256, 512, 384
+    T = Tl * t
+    torch.manual_seed(10 + rank)
+    out = {}
+    # mode 1: all-gather(M) -> GEMM
+    xs = sg.alloc(Tl * H, torch.bfloat16)
+    x_local = torch.randn(Tl, H, device=dev).to(torch.bfloat16)
+    xs.local.view(Tl, H).copy_(x_local)
+    w = (0.05 * torch.randn(n, H, device=dev)).to(torch.bfloat16)
+    parts = [torch.empty_like(x_local) for _ in range(t)]
+    dist.all_gather(parts, x_local)
+    x_full = torch.cat(parts)
+    torch.cuda.synchronize(); dist.barrier()
+    y = torch.empty(T, n, device=dev, dtype=torch.bfloat16)
+    sg.barrier_()
+    C.gemm_dist(1, xs.ptrs, [w.data_ptr()], [y.data_ptr()], T, n, H, H, H, n, True, False, t, rank, Tl)
+    torch.cuda.synchronize()
+    want = x_full.float() @ w.float().t()
+    out["ag_gemm"] = ((y.float() - want).abs().max() / want.abs().max()).item()
+    # mode 2: GEMM -> reduce-scatter push, then reduce
+    a = torch.randn(T, n, device=dev).to(torch.bfloat16)
+    w2 = (0.05 * torch.randn(H, n, device=dev)).to(torch.bfloat16)
+    st = sg.alloc(t * Tl * H, torch.bfloat16)
+    torch.cuda.synchronize(); dist.barrier()
+    C.gemm_dist(2, [a.data_ptr()], [w2.data_ptr()], [p + rank * Tl * H * 2 for p in st.ptrs], T, H, n, n, n, H, True, False,
+                t, rank, Tl)
+    sg.barrier_()
+    red = torch.empty(Tl, H, device=dev, dtype=torch.bfloat16)
+    C.tp_reduce_parts(st.local.view(t, Tl, H), None, red)
+    torch.cuda.synchronize()
+    full = a.float() @ w2.float().t()
+    dist.all_reduce(full)
+    want = full[rank * Tl:(rank + 1) * Tl]
+    out["gemm_rs"] = ((red.float() - want).abs().max() / want.abs().max()).item()
+    # mode 3: wgrad with B gathered along K: dW[n, H] = dy^T[n, T] @ x_full[T, H]
+    dy = torch.randn(T, n, device=dev).to(torch.bfloat16)
+    dw = torch.empty(n, H, device=dev, dtype=torch.bfloat16)
+    C.gemm_dist(3, [dy.data_ptr()], xs.ptrs, [dw.data_ptr()], n, H, T, n, H, H, False, False, t, rank, Tl)
+    torch.cuda.synchronize()
+    want = dy.float().t() @ x_full.float()
+    out["wgrad_b"] = ((dw.float() - want).abs().max() / want.abs().max()).item()
+    # mode 4: wgrad with A gathered along K: dW[H, n] = x_full^T[H, T] @ a[T, n]
+    dw2 = torch.empty(H, n, device=dev, dtype=torch.bfloat16)
+    C.gemm_dist(4, xs.ptrs, [a.data_ptr()], [dw2.data_ptr()], H, n, T, H, n, n, False, False, t, rank, Tl)
+    torch.cuda.synchronize()
+    want = x_full.float().t() @ a.float()
+    out["wgrad_a"] = ((dw2.float() - want).abs().max() / want.abs().max()).item()
+    sg.check()
+    return out
+
+
+def test_distributed_gemm_modes():
+    res = run_distributed(_gemm_modes, world=2, timeout=300)
+    print(res[0])
+    for r in res:
+        for k, v in r.items():
+            assert v < 2e-2, (k, v, r)
+
+
+def _tp_train(rank, world, steps, parallelism, tp):
+    from distributed_training_guide_b200.engine import TrainEngine
+
+    torch.manual_seed(0)
+    eng = TrainEngine.create("debug-llama-tp", parallelism=parallelism, batch_size=2, seq_length=256, lr=1e-3,
+                             tensor_parallel=tp)
+    losses = [float(eng.step(eng.synthetic_batch(seed=i))) for i in range(steps)]
+    eng.close()
+    return losses
+
+
+def test_tensor_parallel_gpu_matches_single_gpu():
+    from distributed_training_guide_b200.engine import TrainEngine
+
+    steps = 3
+    res = run_distributed(_tp_train, world=2, args=(steps, "tp", 2), timeout=300)
+    torch.manual_seed(0)
+    eng = TrainEngine.create("debug-llama-tp", parallelism="single", batch_size=2, seq_length=256, lr=1e-3, device="cuda")
+    ref = [float(eng.step(eng.synthetic_batch(seed=i))) for i in range(steps)]
+    for losses in res:
+        for a, b in zip(losses, ref):
+            assert abs(a - b) < 6e-2, (losses, ref)
+
+
+def _fsdp_train(rank, world, steps):
+    from distributed_training_guide_b200.engine import TrainEngine
+
+    torch.manual_seed(0)
+    eng = TrainEngine.create("debug-llama-gqa", parallelism="fsdp", batch_size=2, seq_length=256, lr=1e-3)
+    losses = [float(eng.step(eng.synthetic_batch(seed=i))) for i in range(steps)]
+    eng.close()
+    return losses
+
+
+def test_fsdp_gpu_matches_single_gpu():
+    from distributed_training_guide_b200.engine import TrainEngine
+
+    steps, world = 3, 2
+    res = run_distributed(_fsdp_train, world=world, args=(steps,), timeout=300)
+    torch.manual_seed(0)
+    eng = TrainEngine.create("debug-llama-gqa", parallelism="single", batch_size=2, seq_length=256, lr=1e-3, device="cuda")
+    ref = []
+    for i in range(steps):
+        parts = []
+        for r in range(world):
+            g = torch.Generator().manual_seed(1000 * i + r)
+            parts.append(torch.randint(0, eng.config.vocab_size, (2, 256), generator=g))
+        ids = torch.cat(parts)
+        ref.append(float(eng.step({"input_ids": ids, "labels": ids.clone()})))
+    for i in range(steps):
+        assert abs(0.5 * (res[0][i] + res[1][i]) - ref[i]) < 6e-2, (i, res, ref)

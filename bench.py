@@ -136,6 +136,7 @@ def run_b200(args):
     dev_batches = [{k: v.to(dev) for k, v in b.items()} for b in host_batches]
     h2d_bytes = sum(v.numel() * v.element_size() for v in host_batches[0].values())
 
+    eng.phase_timing = bool(os.environ.get("DTG_PHASE_TIMING"))
     for i in range(args.warmup):
         eng.step(dev_batches[i % 4])
     # ---- region 1: device-timed steps, batch resident on the GPU --------------------------------
@@ -186,6 +187,7 @@ def run_b200(args):
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
         "final_loss": last,
+        **({"phases_ms": eng.phase_times_ms(last_n=args.steps)} if eng.phase_timing else {}),
         "peak_alloc_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
     }
     if rank == 0:

@@ -34,8 +34,11 @@ constexpr int R_HALF = R_TILE / 2;
 constexpr int C_TILE = 64 * 128 * 2;   // 16 KB streamed tile (two 8 KB halves)
 constexpr int C_HALF = C_TILE / 2;
 constexpr int OFF_R1 = 0, OFF_R2 = R_TILE;
+constexpr int Y_STAGES = 3;                   // TMA ring depth for the streamed tiles: a stage is only
+                                              // released by the gradient MMAs of its block, two stages left
+                                              // the next block's load exposed (~1 TMA latency per block)
 constexpr int OFF_Y = 2 * R_TILE;             // [stage][Y1 | Y2]
-constexpr int OFF_P = OFF_Y + 4 * C_TILE;     // 16 KB: [128 rows x 64] bf16, K-major
+constexpr int OFF_P = OFF_Y + Y_STAGES * 2 * C_TILE;  // 16 KB: [128 rows x 64] bf16, K-major
 constexpr int OFF_DS = OFF_P + 128 * 128;     // 16 KB
 constexpr int OFF_BAR = OFF_DS + 128 * 128;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
@@ -78,13 +81,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* res_full = bars + 0;
-  uint64_t* y_full = bars + 1;     // [2]
-  uint64_t* y_empty = bars + 3;    // [2]
-  uint64_t* sdp_full = bars + 5;   // [2]
-  uint64_t* sdp_empty = bars + 7;  // [2]
-  uint64_t* pds_full = bars + 9;
-  uint64_t* pds_empty = bars + 10;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* y_full = bars + 1;     // [Y_STAGES]
+  uint64_t* y_empty = bars + 5;    // [Y_STAGES]
+  uint64_t* sdp_full = bars + 9;   // [2]
+  uint64_t* sdp_empty = bars + 11; // [2]
+  uint64_t* pds_full = bars + 13;
+  uint64_t* pds_empty = bars + 14;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int group = nh / nkv;
@@ -110,9 +113,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
   }
   if (warp == 1 && elect_one()) {
     mbar_init(res_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < Y_STAGES; ++i) {
       mbar_init(&y_full[i], 1);
       mbar_init(&y_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&sdp_full[i], 1);
       mbar_init(&sdp_empty[i], 8);
     }
@@ -145,8 +150,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
         tma_load_4d(&tm_do_r, res_full, smem + OFF_R2 + R_HALF, 64, head_r, R0, batch);
       }
       for (int t = 0; t < n_iter; ++t) {
-        const int st = t & 1;
-        const uint32_t ph = (uint32_t)((t >> 1) & 1);
+        const int st = t % Y_STAGES;
+        const uint32_t ph = (uint32_t)((t / Y_STAGES) & 1);
         const int c = c_start + (KV_MODE ? t % n_c : t);
         const int C0 = c * 64;
         uint8_t* y1 = smem + OFF_Y + st * 2 * C_TILE;
@@ -174,12 +179,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       const uint32_t r1 = smem_u32(smem + OFF_R1), r2 = smem_u32(smem + OFF_R2);
       const uint32_t sp = smem_u32(smem + OFF_P), sds = smem_u32(smem + OFF_DS);
       auto issue_scores = [&](int t) {
-        const int st = t & 1;
+        const int st = t & 1;                       // S / dP TMEM buffer
         const uint32_t ph = (uint32_t)((t >> 1) & 1);
-        mbar_wait(&y_full[st], ph);
+        const int ys = t % Y_STAGES;                // shared-memory stage of the streamed tiles
+        mbar_wait(&y_full[ys], (uint32_t)((t / Y_STAGES) & 1));
         mbar_wait(&sdp_empty[st], ph ^ 1);
         tc_fence_after();
-        const uint32_t y1 = smem_u32(smem + OFF_Y + st * 2 * C_TILE), y2 = y1 + C_TILE;
+        const uint32_t y1 = smem_u32(smem + OFF_Y + ys * 2 * C_TILE), y2 = y1 + C_TILE;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const uint32_t ra = (uint32_t)((kk >> 2) * R_HALF + (kk & 3) * 32);
@@ -200,10 +206,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       issue_scores(0);
       for (int t = 0; t < n_iter; ++t) {
         if (t + 1 < n_iter) issue_scores(t + 1);
-        const int st = t & 1;
+        const int ys = t % Y_STAGES;
         mbar_wait(pds_full, (uint32_t)(t & 1));
         tc_fence_after();
-        const uint32_t y1 = smem_u32(smem + OFF_Y + st * 2 * C_TILE), y2 = y1 + C_TILE;
+        const uint32_t y1 = smem_u32(smem + OFF_Y + ys * 2 * C_TILE), y2 = y1 + C_TILE;
         if (KV_MODE) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)  // dV += P^T dO_C
@@ -215,7 +221,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
           mma_f16_ss<1>(tmem_base + TM_ACC_B, desc_kmajor_sw128(sds + kk * 32),
                         desc_mnmajor_sw128(y1 + kk * 2048, C_HALF), idesc_g, (t | kk) ? 1u : 0u);
         mma_commit(pds_empty);
-        mma_commit(&y_empty[st]);
+        mma_commit(&y_empty[ys]);
       }
     }
   } else if (warp >= 4) {

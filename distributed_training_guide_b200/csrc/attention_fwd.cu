@@ -171,13 +171,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
       mbar_wait(&s_full[st], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
       float s[64];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(lane_addr + (st ? TM_S1 : TM_S0) + half * 64 + c * 32, r);
+      {
+        uint32_t r0[32], r1[32];  // both loads in flight before the single wait
+        tmem_ld_32x32b_x32(lane_addr + (st ? TM_S1 : TM_S0) + half * 64, r0);
+        tmem_ld_32x32b_x32(lane_addr + (st ? TM_S1 : TM_S0) + half * 64 + 32, r1);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(r[i]);
+        for (int i = 0; i < 32; ++i) {
+          s[i] = __uint_as_float(r0[i]);
+          s[32 + i] = __uint_as_float(r1[i]);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -187,25 +190,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
         for (int i = 0; i < 64; ++i)
           if (half * 64 + i > row) s[i] = -INFINITY;
       }
-      float mx = s[0];
+      float mx4[4] = {s[0], s[1], s[2], s[3]};  // four independent chains instead of one 64-deep one
 #pragma unroll
-      for (int i = 1; i < 64; ++i) mx = fmaxf(mx, s[i]);
+      for (int i = 4; i < 64; i += 4) {
+        mx4[0] = fmaxf(mx4[0], s[i]);
+        mx4[1] = fmaxf(mx4[1], s[i + 1]);
+        mx4[2] = fmaxf(mx4[2], s[i + 2]);
+        mx4[3] = fmaxf(mx4[3], s[i + 3]);
+      }
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       float* redj = red + (j & 1) * 256;
       redj[half * 128 + row] = mx;
       named_bar_sync(1 + q, 64);  // the two warps that share these 32 rows
       mx = fmaxf(m_run, fmaxf(mx, redj[(half ^ 1) * 128 + row]));
       const float alpha = fast_exp2((m_run - mx) * scale_log2);  // 0 on the first block (m_run = -inf)
       const float mb = mx * scale_log2;
-      float sum = 0.f;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t pk[32];
 #pragma unroll
       for (int i = 0; i < 64; i += 2) {
         const float p0 = fast_exp2(fmaf(s[i], scale_log2, -mb));
         const float p1 = fast_exp2(fmaf(s[i + 1], scale_log2, -mb));
-        sum += p0 + p1;
+        sum4[(i >> 1) & 3] += p0 + p1;
         __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
         pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
       }
+      const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
       l_run = l_run * alpha + sum;
       m_run = mx;
       // P_j may only overwrite the shared buffer / O may only be touched once PV_{j-1} is done

@@ -82,17 +82,47 @@ class TrainEngine:
         as a device tensor (reading it is the caller's choice, so the host can run ahead)."""
         s = self.strategy
         dev = self.device
+        ev = self._phase_events() if self.phase_timing else None
         batch = {k: (v.to(dev, non_blocking=True) if v.device != dev else v) for k, v in batch.items()}
         s.pre_step(self.model)
         batch = s.prepare_batch(batch)
+        if ev:
+            ev[0].record()
         out = self.model(**batch)
+        if ev:
+            ev[1].record()
         with s.grad_sync(self.model, enabled=True):
             s.backward(self.model, out.loss)
+        if ev:
+            ev[2].record()
         self.optimizer.step()
         self.lr_scheduler.step()
         self.optimizer.zero_grad(set_to_none=not self.args.cpu_offload)
+        if ev:
+            ev[3].record()
+            self._phase_log.append(ev)
         self.steps_done += 1
         return out.loss.detach()
+
+    # optional per-phase device timing (CUDA events; resolved lazily by phase_times_ms)
+    phase_timing = False
+
+    def _phase_events(self):
+        if not hasattr(self, "_phase_log"):
+            self._phase_log = []
+        return [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def phase_times_ms(self, last_n=None):
+        """Mean forward / backward / update device time of the last ``last_n`` timed steps."""
+        log = getattr(self, "_phase_log", [])
+        log = log[-last_n:] if last_n else log
+        if not log:
+            return {}
+        torch.cuda.synchronize(self.device)
+        f = sum(e[0].elapsed_time(e[1]) for e in log) / len(log)
+        b = sum(e[1].elapsed_time(e[2]) for e in log) / len(log)
+        u = sum(e[2].elapsed_time(e[3]) for e in log) / len(log)
+        return {"forward": f, "backward": b, "update": u}
 
     def synthetic_batch(self, seed: int = 0, pinned: bool = True):
         """A host batch of random tokens of this engine's (batch_size, seq_length); tensor-parallel

@@ -53,6 +53,7 @@ def get_parser(chapter: str = "01-single-gpu", require_experiment: bool = False)
     p.add_argument("--wandb", choices=("off", "rank0", "local-rank0", "all"), default="off",
                    help="reference: related-topics/wandb-configurations")
     p.add_argument("--device", default=None, help="cuda (default when available) or cpu")
+    p.add_argument("--num-workers", default=1, type=int, help="DataLoader worker processes (reference: 1)")
     if "cpu-offload" in extras:
         p.add_argument("--cpu-offload", default=False, action="store_true")
     if "checkpoint-activations" in extras:

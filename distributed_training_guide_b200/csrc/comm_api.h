@@ -6,4 +6,5 @@ namespace dtg {
 void bind_comm(pybind11::module_& m);
 void bind_attention(pybind11::module_& m);
 void bind_tp(pybind11::module_& m);
+void bind_dataloader(pybind11::module_& m);
 }  // namespace dtg

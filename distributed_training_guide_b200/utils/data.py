@@ -117,7 +117,9 @@ def load_and_preprocess_data(args, config, dp_size: int = 1):
         return SyntheticTokens(n, seq_length, config.vocab_size, seed=args.seed)
     if os.path.isfile(name) and name.endswith(".bin"):
         dtype = np.uint16 if config.vocab_size <= 65536 else np.uint32
-        return TokenChunks(np.memmap(name, dtype=dtype, mode="r"), seq_length)
+        ds = TokenChunks(np.memmap(name, dtype=dtype, mode="r"), seq_length)
+        ds.path, ds.vocab_size = name, config.vocab_size  # lets build_dataloader pick the native C++ loader
+        return ds
     if os.path.isfile(name):
         tok = _load_tokenizer(args.model_name)
         if tok is None:
@@ -157,6 +159,39 @@ def _load_hf(args, config, seq_length):
     return lm["train"]
 
 
+class NativeTokenLoader:
+    """Iterable over a ``.bin`` token file served by the C++ loader (``csrc/dataloader.cpp``): mmap + a
+    producer thread filling a ring of pinned [batch, seq] buffers.  Quacks like a DataLoader as far as
+    ``trainer.train`` is concerned (``len``, ``iter``, ``.sampler.set_epoch``)."""
+
+    def __init__(self, path, seq_length, vocab_size, batch_size, dp_size=1, dp_rank=0, seed=0, depth=4):
+        from .. import _ext
+
+        C = _ext.load(required=True)
+        token_bytes = 2 if vocab_size <= 65536 else 4
+        pin = torch.cuda.is_available()
+        self._loader = C.TokenLoader(path, token_bytes, seq_length, batch_size, dp_rank, dp_size, seed, depth, pin)
+        self.sampler = self
+        self._epoch = 0
+        self._started = True  # the constructor already started epoch 0
+
+    def set_epoch(self, epoch):
+        self._epoch = epoch
+        self._loader.set_epoch(epoch)
+        self._started = True
+
+    def __len__(self):
+        return int(self._loader.num_batches())
+
+    def __iter__(self):
+        if not self._started:
+            self._loader.set_epoch(self._epoch)
+        self._started = False
+        for _ in range(len(self)):
+            ids = self._loader.next()
+            yield {"input_ids": ids, "attention_mask": torch.ones_like(ids), "labels": ids}
+
+
 def collate(samples):
     keys = samples[0].keys()
     return {k: torch.stack([torch.as_tensor(s[k]) for s in samples]) for k in keys}
@@ -173,6 +208,12 @@ def build_dataloader(dataset, batch_size, dp_size=1, dp_rank=0, seed=0, distribu
     """Single-process: shuffle + drop_last (``01:62-70``).  Distributed: a
     ``DistributedSampler`` keyed on *data-parallel* coordinates so tensor-parallel peers see
     identical batches (``06:141-147``)."""
+    if isinstance(dataset, TokenChunks) and getattr(dataset, "path", None) is not None:
+        from .. import _ext
+
+        if _ext.available():
+            return NativeTokenLoader(dataset.path, dataset.seq_length, dataset.vocab_size, batch_size, dp_size, dp_rank,
+                                     seed)
     if pin_memory is None:
         pin_memory = torch.cuda.is_available()
     gen = torch.Generator().manual_seed(seed)

@@ -29,14 +29,19 @@ std::tuple<Tensor, Tensor> py_attn_fwd(const Tensor& qkv, int64_t nh, int64_t nk
 }
 
 Tensor py_attn_bwd(const Tensor& d_o, const Tensor& qkv, const Tensor& o, const Tensor& lse, int64_t nh, int64_t nkv,
-                double scale) {
+                   double scale, const c10::optional<Tensor>& trace) {
   check_qkv(qkv, nh, nkv);
   TORCH_CHECK(d_o.is_contiguous() && o.is_contiguous() && d_o.scalar_type() == at::kBFloat16, "dO/O must be contiguous bf16");
   const c10::cuda::CUDAGuard guard(qkv.device());
   const int64_t B = qkv.size(0), S = qkv.size(1);
   Tensor dqkv = torch::empty_like(qkv);
   Tensor delta = torch::empty({B, nh, S}, qkv.options().dtype(at::kFloat));
-  dtg::attn_bwd(qkv.data_ptr(), o.data_ptr(), d_o.data_ptr(), lse.data_ptr<float>(), delta.data_ptr<float>(), nullptr,
+  float* tr = nullptr;
+  if (trace.has_value()) {
+    TORCH_CHECK(trace->scalar_type() == at::kLong && trace->numel() >= 1024, "trace must be int64[1024]");
+    tr = reinterpret_cast<float*>(trace->data_ptr<int64_t>());
+  }
+  dtg::attn_bwd(qkv.data_ptr(), o.data_ptr(), d_o.data_ptr(), lse.data_ptr<float>(), delta.data_ptr<float>(), tr,
                 dqkv.data_ptr(), (int)B, (int)S, (int)nh, (int)nkv, (float)scale,
                 at::cuda::getCurrentCUDAStream().stream());
   return dqkv;
@@ -45,6 +50,7 @@ Tensor py_attn_bwd(const Tensor& d_o, const Tensor& qkv, const Tensor& o, const 
 
 void bind_attention(pybind11::module_& m) {
   m.def("attn_fwd", &py_attn_fwd);
-  m.def("attn_bwd", &py_attn_bwd);
+  m.def("attn_bwd", &py_attn_bwd, pybind11::arg("d_o"), pybind11::arg("qkv"), pybind11::arg("o"), pybind11::arg("lse"),
+        pybind11::arg("nh"), pybind11::arg("nkv"), pybind11::arg("scale"), pybind11::arg("trace") = pybind11::none());
 }
 }  // namespace dtg

@@ -75,8 +75,11 @@ __global__ void __launch_bounds__(bwd::THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_constant__ CUtensorMap tm_qkv_c,
                 const __grid_constant__ CUtensorMap tm_do_r, const __grid_constant__ CUtensorMap tm_do_c,
                 const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
-                int S, int nh, int nkv, float scale, int num_r_blocks) {
+                int S, int nh, int nkv, float scale, int num_r_blocks, long long* __restrict__ trace) {
   using namespace bwd;
+  // optional in-kernel timeline (tools/prof_attn.py --trace): CTA (0,0) records clock64() at the
+  // pipeline hand-over points; columns: [iter][0..3] softmax warp 4, [4..6] MMA thread
+  const bool tracing = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -206,8 +209,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       issue_scores(0);
       for (int t = 0; t < n_iter; ++t) {
         if (t + 1 < n_iter) issue_scores(t + 1);
+        if (tracing && t < 64) trace[t * 8 + 4] = clock64();
         const int ys = t % Y_STAGES;
         mbar_wait(pds_full, (uint32_t)(t & 1));
+        if (tracing && t < 64) trace[t * 8 + 5] = clock64();
         tc_fence_after();
         const uint32_t y1 = smem_u32(smem + OFF_Y + ys * 2 * C_TILE), y2 = y1 + C_TILE;
         if (KV_MODE) {
@@ -222,6 +227,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
                         desc_mnmajor_sw128(y1 + kk * 2048, C_HALF), idesc_g, (t | kk) ? 1u : 0u);
         mma_commit(pds_empty);
         mma_commit(&y_empty[ys]);
+        if (tracing && t < 64) trace[t * 8 + 6] = clock64();
       }
     }
   } else if (warp >= 4) {
@@ -255,7 +261,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
           dq[4 * i] = b.x; dq[4 * i + 1] = b.y; dq[4 * i + 2] = b.z; dq[4 * i + 3] = b.w;
         }
       }
+      const bool tr = tracing && warp == 4 && lane == 0 && t < 64;
       mbar_wait(&sdp_full[st], (uint32_t)((t >> 1) & 1));
+      if (tr) trace[t * 8 + 0] = clock64();
       tc_fence_after();
       uint32_t rs[32], rd[32];
       tmem_ld_32x32b_x32(lane_addr + TM_S + st * 64 + half * 32, rs);
@@ -287,7 +295,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
         pk_p[i >> 1] = *reinterpret_cast<uint32_t*>(&a);
         pk_ds[i >> 1] = *reinterpret_cast<uint32_t*>(&b);
       }
+      if (tr) trace[t * 8 + 1] = clock64();
       if (t > 0) mbar_wait(pds_empty, (uint32_t)((t - 1) & 1));  // gradient MMAs of t-1 released P / dS
+      if (tr) trace[t * 8 + 2] = clock64();
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {  // my 4 chunks of 8 bf16 inside the 64-wide row, 128B swizzle
         const uint32_t off = (uint32_t)((((half * 4 + ch) ^ (r & 7))) << 4);
@@ -300,6 +310,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
+      if (tr) trace[t * 8 + 3] = clock64();
     }
     // write the accumulated gradients of this row (my 64 of the 128 columns)
     mbar_wait(pds_empty, (uint32_t)((n_iter - 1) & 1));
@@ -334,8 +345,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
   if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
 }
 
-void attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta, float* /*unused*/,
+void attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta, float* trace_buf,
               void* dqkv, int B, int S, int nh, int nkv, float scale, cudaStream_t s) {
+  long long* trace = reinterpret_cast<long long*>(trace_buf);  // [2][64][8] int64 or nullptr
   if (S % 128 != 0) throw std::runtime_error("attn_bwd: sequence length must be a multiple of 128");
   const long long rows = (long long)B * S * nh;
   attn_bwd_delta_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(
@@ -352,9 +364,9 @@ void attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse,
   }
   const int nblk = S / 128;
   attn_bwd_kernel<true><<<dim3(B * nkv, nblk, 1), bwd::THREADS, bwd::SMEM_BYTES, s>>>(
-      tq_r, tq_c, td_r, td_c, lse, delta, (__nv_bfloat16*)dqkv, S, nh, nkv, scale, nblk);
+      tq_r, tq_c, td_r, td_c, lse, delta, (__nv_bfloat16*)dqkv, S, nh, nkv, scale, nblk, trace);
   attn_bwd_kernel<false><<<dim3(B * nh, nblk, 1), bwd::THREADS, bwd::SMEM_BYTES, s>>>(
-      tq_r, tq_c, td_r, td_c, lse, delta, (__nv_bfloat16*)dqkv, S, nh, nkv, scale, nblk);
+      tq_r, tq_c, td_r, td_c, lse, delta, (__nv_bfloat16*)dqkv, S, nh, nkv, scale, nblk, trace ? trace + 512 : nullptr);
   note_launch(3);
   DTG_LAUNCH_CHECK();
 }

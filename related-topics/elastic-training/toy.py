@@ -25,9 +25,13 @@ def main():
     ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--failure-prob", type=float, default=0.001)
     ap.add_argument("--step-time", type=float, default=0.01)
+    ap.add_argument("--fail-at-steps", type=int, nargs="*", default=[],
+                    help="deterministic injection: fail once at each of these steps (besides the random failures)")
     args = ap.parse_args()
 
-    dist.init_process_group(backend="gloo")
+    import datetime
+
+    dist.init_process_group(backend="gloo", timeout=datetime.timedelta(seconds=120))
     rank, world = dist.get_rank(), dist.get_world_size()
     state = {"num_steps": 0}
     if os.path.exists(STATE):
@@ -40,7 +44,14 @@ def main():
     random.seed(rank + world * state["num_steps"])
     while state["num_steps"] < args.steps:
         time.sleep(args.step_time)
-        if random.random() < args.failure_prob:
+        planned = state["num_steps"] in args.fail_at_steps and state["num_steps"] not in state.get("failed_at", [])
+        if planned:
+            if rank == 0:  # remember it, so the restarted gang passes this step
+                state.setdefault("failed_at", []).append(state["num_steps"])
+                with open(STATE, "w") as fp:
+                    json.dump(state, fp)
+            dist.barrier()
+        if (planned and rank == state["num_steps"] % world) or random.random() < args.failure_prob:
             raise ValueError(f"injected failure on rank {rank} at step {state['num_steps']}")
         state["num_steps"] += 1
         dist.barrier()

@@ -139,6 +139,26 @@ def run_b200(args):
     eng.phase_timing = bool(os.environ.get("DTG_PHASE_TIMING"))
     for i in range(args.warmup):
         eng.step(dev_batches[i % 4])
+    if os.environ.get("DTG_CPU_PROFILE") and rank == 0:  # host-side cost of one step (diagnostics)
+        import cProfile
+        import io
+        import pstats
+
+        torch.cuda.synchronize(dev)
+        pr = cProfile.Profile()
+        t0 = time.perf_counter()
+        pr.enable()
+        eng.step(dev_batches[0])
+        pr.disable()
+        host_ms = 1000 * (time.perf_counter() - t0)
+        torch.cuda.synchronize(dev)
+        buf = io.StringIO()
+        pstats.Stats(pr, stream=buf).sort_stats("cumulative").print_stats(45)
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open(os.environ["DTG_CPU_PROFILE"], "w") as fp:
+            fp.write(f"host time to enqueue one step: {host_ms:.1f} ms\n" + buf.getvalue())
+    elif os.environ.get("DTG_CPU_PROFILE"):
+        eng.step(dev_batches[0])
     # ---- region 1: device-timed steps, batch resident on the GPU --------------------------------
     _barrier_sync(dev)
     l0 = _ext.launch_count()

@@ -45,6 +45,10 @@ void gemm_bf16_dist(int mode, const void* const* a_srcs, const void* const* b_sr
                     int K, long long lda, long long ldb, long long ldc, bool b_kmajor, bool accumulate, int nranks,
                     int rank, int rows_per_peer, cudaStream_t s);
 
+void gemm_bf16_ag(const void* const* a_bufs, const void* B, void* C, int M, int N, int K, long long ldb, long long ldc,
+                  bool b_kmajor, int nranks, int rank, int rows_per_peer, uint32_t* flags, uint32_t ag_epoch,
+                  uint32_t* const* pads, uint32_t bar_epoch, int n_comm, cudaStream_t s);
+
 // ---- attention.cu --------------------------------------------------------------------------
 // qkv: [B,S,nh+2*nkv,128] bf16 (q heads | k heads | v heads); o: [B,S,nh,128]; lse: [B,nh,S] fp32
 void attn_fwd(const void* qkv, void* o, float* lse, int B, int S, int nh, int nkv, float scale, cudaStream_t s);

@@ -37,12 +37,44 @@ struct GemmDist {
   int m_tile_shift;                  // rotate the M tile order so every rank starts on its own rows
   int k_shift;                       // rotate the K block order likewise
   __nv_bfloat16* c_ptr[kMaxRanks];   // C_MODE 1: destination base (already offset to my slot) per owner
+  // A_MODE 3 (all-gather by communication CTAs inside the GEMM kernel)
+  const char* ag_src[kMaxRanks];     // the symmetric [M, K] buffer on every rank, ROTATED: [0] = mine
+  uint32_t* ag_flags;                // local: one word per 256-row tile, set to ag_epoch once the tile landed
+  uint32_t ag_epoch;
+  uint32_t* pads[kMaxRanks];         // signal pads (not rotated) for the start-of-kernel barrier
+  uint32_t bar_epoch;
+  int n_comm;                        // clusters (CTA pairs) that copy instead of multiplying
+  int rank, nranks;
+  long long tile_bytes;              // bytes of one 256-row tile of A (contiguous: lda == K)
 };
 
 #ifdef __CUDACC__
 __device__ __forceinline__ int tile_m(int t, int num_m_tiles, const GemmDist& d) {
   int m = t % num_m_tiles + d.m_tile_shift;
   return m >= num_m_tiles ? m - num_m_tiles : m;
+}
+// Tile order.  Default: M fastest (consecutive CTAs share the B tile).  With an in-kernel all-gather
+// (`local_m_tiles` > 0): first every tile of my own rows (pure local work while the communication CTAs
+// fetch), then the remote row tiles in the order they are being fetched.
+__device__ __forceinline__ void tile_mn(int t, int num_m_tiles, const GemmDist& d, int local_m_tiles, int& m, int& n) {
+  if (local_m_tiles <= 0) {
+    m = tile_m(t, num_m_tiles, d);
+    n = t / num_m_tiles;
+    return;
+  }
+  const int num_n = d.k_shift;  // reused field: number of N tiles (K is never gathered in this mode)
+  const int phase_a = local_m_tiles * num_n;
+  int mm;
+  if (t < phase_a) {
+    mm = t % local_m_tiles;
+    n = t / local_m_tiles;
+  } else {
+    const int u = t - phase_a, rest = num_m_tiles - local_m_tiles;
+    mm = local_m_tiles + u % rest;
+    n = u / rest;
+  }
+  mm += d.m_tile_shift;
+  m = mm >= num_m_tiles ? mm - num_m_tiles : mm;
 }
 #endif
 

@@ -34,6 +34,11 @@ using namespace ptx;
 //                    (all-gather -> GEMM);  2 = the reduction dimension K gathered from the ranks (wgrad
 //                    over a sequence-sharded activation).  Tiles are fetched from the owning peer by TMA
 //                    over NVLink, so the transfer streams under the MMA pipeline.
+//                    3 = all-gather by COMMUNICATION CTAs of this same kernel: the first `n_comm` CTA pairs
+//                    bulk-copy (cp.async.bulk, NVLink -> smem -> local HBM) the peers' row tiles into the
+//                    local [M, K] buffer and publish a per-tile flag; the GEMM CTAs start on the local rows and
+//                    acquire the flag before their TMA touches a fetched tile.  Each remote byte crosses NVLink
+//                    exactly once (peer memory bypasses the local L2, so mode 1 re-fetches it per N tile).
 //   C_MODE           0 = local C;  1 = each `rows_per_peer` row chunk of C is stored into its owner's
 //                    staging buffer (GEMM -> reduce-scatter push).
 template <bool A_K, bool B_K, int CG, int A_MODE = 0, int B_MODE = 0, int C_MODE = 0>
@@ -51,14 +56,18 @@ gemm_bf16_kernel(const __grid_constant__ TmapSet<(A_MODE ? kMaxRanks : 1)> tmAs,
   uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* comm_bar = tmem_empty + 4;  // [STAGES] used only by communication CTAs (A_MODE 3)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool is_leader = cta_rank == 0;
-  const int cluster_id = blockIdx.x / CG;
-  const int num_clusters = gridDim.x / CG;
+  const int n_comm = (A_MODE == 3) ? dist.n_comm : 0;
+  const bool is_comm = (A_MODE == 3) && (int)(blockIdx.x / CG) < n_comm;
+  const int cluster_id = (int)(blockIdx.x / CG) - n_comm;       // index among the GEMM clusters
+  const int num_clusters = (int)(gridDim.x / CG) - n_comm;
   const int num_kb = (K + Cfg::BK - 1) / Cfg::BK;
+  const int local_m_tiles = (A_MODE == 3) ? dist.rows_per_peer / (Cfg::BM * CG) : 0;
 
   if (warp == 0 && elect_one()) {
     prefetch_tensormap(&tmAs.m[0]);
@@ -73,6 +82,8 @@ gemm_bf16_kernel(const __grid_constant__ TmapSet<(A_MODE ? kMaxRanks : 1)> tmAs,
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 4 * CG);
     }
+    if constexpr (A_MODE == 3)
+      for (int i = 0; i < Cfg::STAGES; ++i) mbar_init(&comm_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -84,16 +95,74 @@ gemm_bf16_kernel(const __grid_constant__ TmapSet<(A_MODE ? kMaxRanks : 1)> tmAs,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp == 0) {
+  if (is_comm) {
+    // ===================== communication CTA: all-gather the peers' row tiles =====================
+    if (warp == 0 && elect_one()) {
+      const int cidx = (int)blockIdx.x;  // 0 .. n_comm*CG-1 : also my signal-pad channel
+      const int ncta = n_comm * CG;
+      const int t_ = dist.nranks, rk = dist.rank;
+      // every rank's activation shard is written once its kernel has started (stream order)
+      for (int p = 0; p < t_; ++p) st_release_sys(dist.pads[p] + cidx * kMaxRanks + rk, dist.bar_epoch);
+      for (int p = 0; p < t_; ++p) {
+        const uint32_t* mine = dist.pads[rk] + cidx * kMaxRanks + p;
+        const long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(mine) - dist.bar_epoch) < 0)
+          if (clock64() - t0 > 20000000000LL) break;
+      }
+      constexpr uint32_t PIECE = Cfg::STAGE_BYTES;   // one ring slot = one pipeline stage of the GEMM smem
+      constexpr int NB = Cfg::STAGES, AHEAD = NB - 2;
+      const int lmt = local_m_tiles > 0 ? local_m_tiles : 1;
+      const int remote_tiles = (t_ - 1) * lmt;
+      const uint32_t pieces_per_tile = (uint32_t)(dist.tile_bytes / PIECE);
+      uint32_t issued = 0, stored = 0;  // global piece counters (ring position / barrier parity)
+      for (int r = cidx; r < remote_tiles; r += ncta) {
+        const int k = 1 + r / lmt, within = r % lmt;
+        const int owner = (rk + k) % t_;
+        const int m_tile = owner * lmt + within;
+        const char* src = dist.ag_src[k] + (long long)m_tile * dist.tile_bytes;
+        char* dst = const_cast<char*>(dist.ag_src[0]) + (long long)m_tile * dist.tile_bytes;
+        uint32_t li = 0;  // pieces of this tile whose load has been issued
+        for (uint32_t si = 0; si < pieces_per_tile; ++si) {
+          while (li < pieces_per_tile && li < si + AHEAD) {
+            const uint32_t slot = issued % NB;
+            // the bulk store that last read this slot was committed >= 2 stores ago
+            bulk_wait_group_read<1>();
+            mbar_arrive_expect_tx(&comm_bar[slot], PIECE);
+            bulk_load_g2s(smem + slot * PIECE, src + (long long)li * PIECE, PIECE, &comm_bar[slot]);
+            ++issued;
+            ++li;
+          }
+          const uint32_t slot = stored % NB;
+          mbar_wait(&comm_bar[slot], (stored / NB) & 1);
+          bulk_store_s2g(dst + (long long)si * PIECE, smem + slot * PIECE, PIECE);
+          bulk_commit_group();
+          ++stored;
+        }
+        bulk_wait_group<0>();       // the whole tile is in local memory
+        fence_proxy_async_all();
+        st_release_gpu(dist.ag_flags + m_tile, dist.ag_epoch);
+      }
+    }
+  } else if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        const int m0 = tile_m(t, num_m_tiles, dist) * (Cfg::BM * CG) + (int)cta_rank * Cfg::BM;
-        const int nb = (t / num_m_tiles) * Cfg::BN + (int)cta_rank * Cfg::B_ROWS;
+        int tm_, tn_;
+        tile_mn(t, num_m_tiles, dist, local_m_tiles, tm_, tn_);
+        const int m0 = tm_ * (Cfg::BM * CG) + (int)cta_rank * Cfg::BM;
+        const int nb = tn_ * Cfg::BN + (int)cta_rank * Cfg::B_ROWS;
         const CUtensorMap* tmA_p = &tmAs.m[0];
         int a_m0 = m0;
+        if constexpr (A_MODE == 3) {  // fetched tile: wait until the communication CTAs published it
+          if (tm_ / (local_m_tiles > 0 ? local_m_tiles : 1) != dist.rank) {
+            const long long t0 = clock64();
+            while ((int32_t)(ld_acquire_gpu(dist.ag_flags + tm_) - dist.ag_epoch) < 0)
+              if (clock64() - t0 > 20000000000LL) break;
+            fence_proxy_async_all();
+          }
+        }
         if constexpr (A_MODE == 1) {  // this row block lives on rank m0 / rows_per_peer
           const int peer = m0 / dist.rows_per_peer;
           tmA_p = &tmAs.m[peer];
@@ -155,7 +224,7 @@ gemm_bf16_kernel(const __grid_constant__ TmapSet<(A_MODE ? kMaxRanks : 1)> tmAs,
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && !is_comm) {
     // ===================== MMA issuer (leader CTA) =====================
     if (is_leader && elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(Cfg::BM * CG, Cfg::BN, !A_K, !B_K);
@@ -185,14 +254,16 @@ gemm_bf16_kernel(const __grid_constant__ TmapSet<(A_MODE ? kMaxRanks : 1)> tmAs,
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && !is_comm) {
     // ===================== epilogue: TMEM -> registers -> global =====================
     const int q = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-      const int m0 = tile_m(t, num_m_tiles, dist) * (Cfg::BM * CG) + (int)cta_rank * Cfg::BM;
-      const int n0 = (t / num_m_tiles) * Cfg::BN;
+      int tm_, tn_;
+      tile_mn(t, num_m_tiles, dist, local_m_tiles, tm_, tn_);
+      const int m0 = tm_ * (Cfg::BM * CG) + (int)cta_rank * Cfg::BM;
+      const int n0 = tn_ * Cfg::BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
@@ -318,8 +389,8 @@ static void launch_gemm(const void* const* a_srcs, const void* const* b_srcs, vo
   TmapSet<(A_MODE ? kMaxRanks : 1)> tmA;
   TmapSet<(B_MODE ? kMaxRanks : 1)> tmB;
   const int rpp = dist.rows_per_peer;
-  for (int p = 0; p < (A_MODE ? nranks : 1); ++p) {
-    const int rows = (A_MODE == 1) ? rpp : M;   // M extent of this source
+  for (int p = 0; p < ((A_MODE == 1 || A_MODE == 2) ? nranks : 1); ++p) {
+    const int rows = (A_MODE == 1) ? rpp : M;   // M extent of this source (mode 3: the local gathered buffer)
     const int ks = (A_MODE == 2) ? rpp : K;     // K extent of this source
     tmA.m[p] = A_K ? make_tmap_2d(a_srcs[p], ks, rows, lda * 2, 64, Cfg::BM) : make_tmap_2d(a_srcs[p], rows, ks, lda * 2, 64, 64);
   }
@@ -327,7 +398,7 @@ static void launch_gemm(const void* const* a_srcs, const void* const* b_srcs, vo
     const int ks = (B_MODE == 2) ? rpp : K;
     tmB.m[p] = B_K ? make_tmap_2d(b_srcs[p], ks, N, ldb * 2, 64, Cfg::B_ROWS) : make_tmap_2d(b_srcs[p], N, ks, ldb * 2, 64, 64);
   }
-  for (int p = (A_MODE ? nranks : 1); p < (A_MODE ? kMaxRanks : 1); ++p) tmA.m[p] = tmA.m[0];
+  for (int p = ((A_MODE == 1 || A_MODE == 2) ? nranks : 1); p < (A_MODE ? kMaxRanks : 1); ++p) tmA.m[p] = tmA.m[0];
   for (int p = (B_MODE ? nranks : 1); p < (B_MODE ? kMaxRanks : 1); ++p) tmB.m[p] = tmB.m[0];
   const int num_m_tiles = (M + Cfg::BM * CG - 1) / (Cfg::BM * CG);
   const int num_n_tiles = (N + Cfg::BN - 1) / Cfg::BN;
@@ -339,7 +410,14 @@ static void launch_gemm(const void* const* a_srcs, const void* const* b_srcs, vo
     attr_set = true;
   }
   int clusters = sm_count() / CG;
-  if (clusters > num_tiles) clusters = num_tiles;
+  if constexpr (A_MODE == 3) {
+    dist.k_shift = num_n_tiles;  // tile_mn() needs the N tile count in this mode
+    int gemm_clusters = clusters - dist.n_comm;
+    if (gemm_clusters > num_tiles) gemm_clusters = num_tiles;
+    clusters = gemm_clusters + dist.n_comm;
+  } else if (clusters > num_tiles) {
+    clusters = num_tiles;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * CG);
   cfg.blockDim = dim3(256);
@@ -452,6 +530,35 @@ void gemm_bf16_dist(int mode, const void* const* a_srcs, const void* const* b_sr
     default:
       throw std::runtime_error("gemm_bf16_dist: unknown mode");
   }
+}
+
+
+// all-gather -> GEMM with the gather done by communication CTAs of the same kernel (A_MODE 3).
+//   a_bufs[p]: rank p's symmetric [M, K] buffer (its own rows_per_peer rows are valid); a_bufs[rank] is also the
+//   destination of the gather.  flags: local uint32 [M / 256].  pads: the group's signal pads.
+void gemm_bf16_ag(const void* const* a_bufs, const void* B, void* C, int M, int N, int K, long long ldb, long long ldc,
+                  bool b_kmajor, int nranks, int rank, int rows_per_peer, uint32_t* flags, uint32_t ag_epoch,
+                  uint32_t* const* pads, uint32_t bar_epoch, int n_comm, cudaStream_t s) {
+  constexpr int TM = GemmCfg<2>::BM * 2;
+  if (rows_per_peer % TM != 0 || rows_per_peer * nranks != M) throw std::runtime_error("gemm_bf16_ag: bad row split");
+  if ((K * 2LL * TM) % GemmCfg<2>::STAGE_BYTES != 0) throw std::runtime_error("gemm_bf16_ag: K must be a multiple of 64");
+  if ((N % 8) || (ldc % 8) || (ldb % 8)) throw std::runtime_error("gemm_bf16_ag: N / leading dims must be multiples of 8");
+  GemmDist dist{};
+  dist.rows_per_peer = rows_per_peer;
+  dist.m_tile_shift = rank * (rows_per_peer / TM);
+  for (int k = 0; k < nranks; ++k) dist.ag_src[k] = (const char*)a_bufs[(rank + k) % nranks];
+  for (int p = 0; p < nranks; ++p) dist.pads[p] = pads[p];
+  dist.ag_flags = flags;
+  dist.ag_epoch = ag_epoch;
+  dist.bar_epoch = bar_epoch;
+  dist.n_comm = n_comm < 1 ? 1 : n_comm;
+  dist.rank = rank;
+  dist.nranks = nranks;
+  dist.tile_bytes = (long long)TM * K * 2;
+  const void* as[1] = {a_bufs[rank]};
+  const void* bs[1] = {B};
+  if (b_kmajor) launch_gemm<true, true, 2, 3, 0, 0>(as, bs, C, M, N, K, K, ldb, ldc, false, dist, nranks, s);
+  else launch_gemm<true, false, 2, 3, 0, 0>(as, bs, C, M, N, K, K, ldb, ldc, false, dist, nranks, s);
 }
 
 }  // namespace dtg

@@ -37,6 +37,29 @@ void py_gemm_dist(int64_t mode, const std::vector<uint64_t>& a_ptrs, const std::
                       (int)rank, (int)rows_per_peer, stream());
 }
 
+void py_gemm_ag(const std::vector<uint64_t>& a_bufs, const Tensor& b, Tensor& out, bool b_kmajor, int64_t rank,
+                int64_t rows_per_peer, Tensor& flags, int64_t ag_epoch, const std::vector<uint64_t>& pads,
+                int64_t bar_epoch, int64_t n_comm) {
+  TORCH_CHECK(b.is_cuda() && b.scalar_type() == at::kBFloat16 && b.dim() == 2 && b.stride(1) == 1, "bad B");
+  TORCH_CHECK(out.is_cuda() && out.scalar_type() == at::kBFloat16 && out.dim() == 2 && out.stride(1) == 1, "bad out");
+  TORCH_CHECK(flags.scalar_type() == at::kInt && flags.is_cuda(), "flags must be an int32 CUDA tensor");
+  const c10::cuda::CUDAGuard guard(out.device());
+  const int nr = (int)a_bufs.size();
+  const int M = (int)out.size(0), N = (int)out.size(1);
+  const int K = (int)(b_kmajor ? b.size(1) : b.size(0));
+  TORCH_CHECK((b_kmajor ? b.size(0) : b.size(1)) == N, "B does not match out");
+  TORCH_CHECK(flags.numel() * 256 >= M, "flags too small");
+  const void* as[kMaxRanks] = {nullptr};
+  uint32_t* pd[kMaxRanks] = {nullptr};
+  for (int i = 0; i < nr; ++i) {
+    as[i] = (const void*)a_bufs[i];
+    pd[i] = (uint32_t*)pads[i];
+  }
+  dtg::gemm_bf16_ag(as, b.data_ptr(), out.data_ptr(), M, N, K, b.stride(0), out.stride(0), b_kmajor, nr, (int)rank,
+                    (int)rows_per_peer, (uint32_t*)flags.data_ptr<int>(), (uint32_t)ag_epoch, pd, (uint32_t)bar_epoch,
+                    (int)n_comm, stream());
+}
+
 void py_reduce_parts(const Tensor& parts, const c10::optional<Tensor>& residual, Tensor& out) {
   TORCH_CHECK(parts.is_contiguous() && out.is_contiguous() && parts.scalar_type() == at::kBFloat16, "bad tensors");
   const int64_t nparts = parts.size(0);
@@ -82,6 +105,7 @@ void py_embed_bwd(const Tensor& ids, const std::vector<uint64_t>& dx_ptrs, Tenso
 
 void bind_tp(pybind11::module_& m) {
   m.def("gemm_dist", &py_gemm_dist);
+  m.def("gemm_ag", &py_gemm_ag);
   m.def("tp_reduce_parts", &py_reduce_parts);
   m.def("vp_ce_stats", &py_vp_ce_stats);
   m.def("vp_ce_grad", &py_vp_ce_grad);

@@ -49,11 +49,19 @@ class TPContext:
         self.rpp = max_tokens // tp_size  # rows (tokens) per rank
         self.n_layers = n_layers
         if self.use_kernels:
+            import os
+
             Tl, H = self.rpp, hidden
-            # saved column-parallel inputs: [layer][attn-in | mlp-in] + final-norm output for lm_head
-            self.act = symm.alloc((2 * n_layers + 1) * Tl * H, dtype)
+            T = max_tokens
+            # column-parallel inputs, one FULL [T, H] slot per use ([layer][attn-in | mlp-in] + lm_head input):
+            # a rank writes its own rows, the all-gather->GEMM kernel fetches the others into the same slot and
+            # the gathered copy is what the weight-gradient GEMM reads in backward (no second gather)
+            self.act = symm.alloc((2 * n_layers + 1) * T * H, dtype)
             self.stage = [symm.alloc(tp_size * Tl * H, dtype) for _ in range(2)]  # reduce-scatter landing zones
-            self.gbuf = [symm.alloc(Tl * H, dtype) for _ in range(2)]            # grads w.r.t. row-parallel outputs
+            self.gbuf = [symm.alloc(T * H, dtype) for _ in range(2)]             # gathered grads of row-parallel outputs
+            self.flags = torch.zeros(max(1, T // 256), dtype=torch.int32, device=device)
+            self.ag_epoch = 0
+            self.n_comm = int(os.environ.get("DTG_TP_COMM_CLUSTERS", "4"))
             self.x0 = symm.alloc(Tl * H, dtype)    # embedding output (all-to-all target)
             self.dx0 = symm.alloc(Tl * H, dtype)   # its gradient
             self.stats = symm.alloc(max_tokens * 4, torch.float32)
@@ -62,8 +70,17 @@ class TPContext:
 
     # symmetric slices ---------------------------------------------------------------------------
     def act_slot(self, idx):
-        n = self.rpp * self.H
-        return self.act.local[idx * n:(idx + 1) * n].view(self.rpp, self.H), [p + idx * n * 2 for p in self.act.ptrs]
+        """(full [T, H] view of slot idx, view of my rows inside it, per-rank base pointers of the slot)."""
+        n = self.max_tokens * self.H
+        full = self.act.local[idx * n:(idx + 1) * n].view(self.max_tokens, self.H)
+        mine = full[self.rank * self.rpp:(self.rank + 1) * self.rpp]
+        return full, mine, [p + idx * n * 2 for p in self.act.ptrs]
+
+    def gather_gemm(self, bufs, b, out, b_kmajor):
+        """out = all_gather_rows(symmetric buffer) @ op(b): ONE kernel, the gather runs on communication CTAs."""
+        self.ag_epoch += 1
+        self.symm.C.gemm_ag(bufs, b, out, b_kmajor, self.rank, self.rpp, self.flags, self.ag_epoch, self.symm.pad_ptrs,
+                            self.symm._epochs(1), self.n_comm)
 
     def next_stage(self):
         b = self.stage[self._stage_i]
@@ -119,13 +136,10 @@ class _ColumnParallelLinear(torch.autograd.Function):
             xf = tp.all_gather_rows(x_local)
             ctx.save_for_backward(x_local, w)
             return xf @ w.t()
-        C = _ext.load()
-        buf, ptrs = tp.act_slot(slot)
-        buf.copy_(x_local)           # my sequence shard, where the peers' TMA can reach it
-        tp.barrier()                 # every rank's shard is in place
+        full, mine, ptrs = tp.act_slot(slot)
+        mine.copy_(x_local)          # my sequence shard, where the peers' copy engines can reach it
         out = torch.empty(T, n, dtype=x_local.dtype, device=x_local.device)
-        C.gemm_dist(1, ptrs, [w.data_ptr()], [out.data_ptr()], T, n, H, H, w.stride(0), n, True, False, tp.t, tp.rank,
-                    tp.rpp)
+        tp.gather_gemm(ptrs, w, out, True)   # barrier + all-gather + GEMM in one kernel; `full` is now complete
         ctx.save_for_backward(w)
         return out
 
@@ -143,13 +157,12 @@ class _ColumnParallelLinear(torch.autograd.Function):
         C = _ext.load()
         (w,) = ctx.saved_tensors
         H = w.shape[1]
-        _, ptrs = tp.act_slot(ctx.slot)
-        # wgrad: dW[n, H] (+)= dy^T[n, T] @ x_full[T, H]   (x gathered along K from the peers' saved shards)
+        full, _, _ = tp.act_slot(ctx.slot)
+        # wgrad: dW[n, H] (+)= dy^T[n, T] @ x_full[T, H]   (the copy gathered by the forward kernel)
         gbuf = owner._dtg_grad
         acc = owner._dtg_writes > 0
         owner._dtg_writes += 1
-        C.gemm_dist(3, [dy.data_ptr()], ptrs, [gbuf.data_ptr()], n, H, T, n, H, gbuf.stride(0), False, acc, tp.t,
-                    tp.rank, tp.rpp)
+        ops.gemm(dy, full, out=gbuf, trans_a=True, accumulate=acc)
         # dgrad: partial dx[T, H] = dy[T, n] @ W[n, H], pushed row-chunk-wise to the owners, then summed
         st = tp.next_stage()
         Tl = tp.rpp
@@ -212,20 +225,17 @@ class _RowParallelLinear(torch.autograd.Function):
             dx = dyf @ w
             dw = dyf.t() @ x
             return dx, dw if owner is None else _route_dw(owner, dw), None, None, dres
-        C = _ext.load()
         gb = tp.next_gbuf()
-        gb.local.view(tp.rpp, H).copy_(dy_local)
-        tp.barrier()
-        # dgrad: dx[T, k] = all_gather_rows(dy)[T, H] @ W[H, k]
+        gfull = gb.local.view(T, H)
+        gfull[tp.rank * tp.rpp:(tp.rank + 1) * tp.rpp].copy_(dy_local)
+        # dgrad: dx[T, k] = all_gather_rows(dy)[T, H] @ W[H, k]   (gather + GEMM in one kernel)
         dx = torch.empty(T, k, dtype=x.dtype, device=x.device)
-        C.gemm_dist(1, gb.ptrs, [w.data_ptr()], [dx.data_ptr()], T, k, H, H, w.stride(0), k, False, False, tp.t, tp.rank,
-                    tp.rpp)
-        # wgrad: dW[H, k] (+)= dy_full^T[H, T] @ x[T, k]   (dy gathered along K)
+        tp.gather_gemm(gb.ptrs, w, dx, False)
+        # wgrad: dW[H, k] (+)= dy_full^T[H, T] @ x[T, k]   (reads the copy the dgrad kernel gathered)
         gbuf = owner._dtg_grad
         acc = owner._dtg_writes > 0
         owner._dtg_writes += 1
-        C.gemm_dist(4, gb.ptrs, [x.data_ptr()], [gbuf.data_ptr()], H, k, T, H, x.stride(0), gbuf.stride(0), False, acc,
-                    tp.t, tp.rank, tp.rpp)
+        ops.gemm(gfull, x, out=gbuf, trans_a=True, accumulate=acc)
         return dx, None, None, None, dres
 
 

@@ -67,6 +67,33 @@ def _gemm_modes(rank, world):
     torch.cuda.synchronize()
     want = x_full.float().t() @ a.float()
     out["wgrad_a"] = ((dw2.float() - want).abs().max() / want.abs().max()).item()
+    # in-kernel all-gather by communication CTAs (bulk copies over NVLink + per-tile flags) -> GEMM
+    Tl2, H2, n2 = 512, 1024, 768            # two 256-row tiles per rank, 32 KB pieces
+    T2 = Tl2 * t
+    ag = sg.alloc(T2 * H2, torch.bfloat16)
+    full = ag.local.view(T2, H2)
+    full.zero_()
+    xl = torch.randn(Tl2, H2, device=dev).to(torch.bfloat16)
+    full[rank * Tl2:(rank + 1) * Tl2].copy_(xl)
+    parts = [torch.empty_like(xl) for _ in range(t)]
+    dist.all_gather(parts, xl)
+    xf = torch.cat(parts)
+    flags = torch.zeros(T2 // 256, dtype=torch.int32, device=dev)
+    for ep, (wm, bk) in enumerate([((0.05 * torch.randn(n2, H2, device=dev)).to(torch.bfloat16), True),
+                                   ((0.05 * torch.randn(H2, n2, device=dev)).to(torch.bfloat16), False)], start=1):
+        if ep == 2:  # second call: fresh data in my rows, stale gathered rows must be re-fetched
+            xl = torch.randn(Tl2, H2, device=dev).to(torch.bfloat16)
+            torch.cuda.synchronize(); dist.barrier()
+            full[rank * Tl2:(rank + 1) * Tl2].copy_(xl)
+            dist.all_gather(parts, xl)
+            xf = torch.cat(parts)
+        y2 = torch.empty(T2, n2, device=dev, dtype=torch.bfloat16)
+        torch.cuda.synchronize(); dist.barrier()
+        C.gemm_ag(ag.ptrs, wm, y2, bk, rank, Tl2, flags, ep, sg.pad_ptrs, sg._epochs(1), 2)
+        torch.cuda.synchronize()
+        want = xf.float() @ (wm.float().t() if bk else wm.float())
+        out[f"gemm_ag_{ep}"] = ((y2.float() - want).abs().max() / want.abs().max()).item()
+        out[f"gathered_copy_{ep}"] = (full.float() - xf.float()).abs().max().item()
     sg.check()
     return out
 

@@ -17,7 +17,7 @@ import torch
 from .models import get_config
 from .utils.lr import scale_lr
 
-PARALLELISMS = ("single", "ddp", "fsdp", "tp", "2d")
+PARALLELISMS = ("single", "ddp", "ddp_allreduce", "fsdp", "tp", "2d")
 
 
 def make_strategy(parallelism: str, args):
@@ -27,6 +27,8 @@ def make_strategy(parallelism: str, args):
         return S.SingleDevice(args)
     if parallelism == "ddp":
         return S.DataParallelZero1(args)
+    if parallelism == "ddp_allreduce":  # plain DDP: fused scale + all-reduce buckets, unsharded optimizer
+        return S.DataParallelZero1(args, zero1=False)
     if parallelism == "fsdp":
         return S.FullyShardedDataParallel(args)
     if parallelism == "tp":

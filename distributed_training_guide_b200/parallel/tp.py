@@ -10,13 +10,16 @@ NCCL all-gather / reduce-scatter / all-to-all sitting on the critical path of ev
 Here the activations between blocks are sequence shards ``[T/t, H]`` living in NVLink-symmetric
 buffers, and the collectives disappear into the tensor-core kernels:
 
-  * column-parallel linear = ONE tcgen05 GEMM whose A tiles are fetched by TMA from the rank that owns
-    those rows (all-gather -> GEMM, ``gemm_dist`` mode 1);
+  * column-parallel linear = ONE tcgen05 GEMM kernel in which a few communication CTAs bulk-copy the
+    peers' row tiles over NVLink into the local gathered buffer and publish per-tile flags, while the
+    GEMM CTAs start on the local rows and acquire a tile's flag before their TMA reads it (all-gather ->
+    GEMM, ``gemm_ag``; a variant that TMA-loads every tile from its owner, ``gemm_dist`` mode 1, re-fetches
+    remote tiles once per N tile because peer memory bypasses the local L2);
   * row-parallel linear = ONE GEMM whose epilogue stores each row chunk straight into the owner's
     staging slot (GEMM -> reduce-scatter, mode 2); the owner sums the t partials (+ residual) in the
     kernel that feeds the next RMSNorm;
-  * their weight gradients contract over the full sequence with the sequence-sharded operand gathered
-    along K inside the GEMM (modes 3 / 4), no re-materialised all-gather;
+  * their weight gradients contract over the full sequence and read the copy the forward (resp. dgrad)
+    kernel gathered, so backward needs no second all-gather (K-gathered GEMM modes 3 / 4 also exist);
   * lm_head logits stay vocabulary-sharded and the loss is a vocab-parallel cross entropy (the
     "loss parallel" the reference only documents, ``06-tensor-parallel/README.md:241-271``);
   * the embedding is hidden-sharded and its all-to-all is fused into the lookup kernel.

@@ -39,9 +39,13 @@ def _single_reference(steps, world):
     return losses, {k: v.detach().float().clone() for k, v in eng.model.state_dict().items()}
 
 
-def test_ddp_zero1_matches_single_process():
+import pytest
+
+
+@pytest.mark.parametrize("parallelism", ["ddp", "ddp_allreduce"])
+def test_ddp_matches_single_process(parallelism):
     steps, world = 3, 2
-    res = run_distributed(_train, world=world, args=("ddp", steps, True))
+    res = run_distributed(_train, world=world, args=(parallelism, steps, True))
     ref_losses, ref_sd = _single_reference(steps, world)
     (l0, sd0, _), (l1, sd1, _) = res
     # replicas stay identical

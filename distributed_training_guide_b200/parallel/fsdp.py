@@ -328,6 +328,9 @@ class FSDPEngine:
             else:
                 gshard = g.grad.float()
             st["step"] += 1
+            if self.cpu_offload:  # the update itself happens in optimizer.step() on the host copies
+                st["cpu_grad"].copy_((gshard * opt.grad_scale).to(st["cpu_grad"].dtype))
+                return
             lr, b1, b2, eps, wd = opt.hyper()
             ref.adamw_step(sh.param, gshard.to(sh.param.dtype), st["exp_avg"], st["exp_avg_sq"], lr, b1, b2, eps, wd,
                            st["step"], opt.grad_scale)

@@ -371,17 +371,33 @@ class TwoDParallel(Strategy):
         ctx = self.tp_ctx
         if ctx.t == 1:
             return
-        for off, n in self._norm_regions(g):
-            view = g.grad[off:off + n]
-            if ctx.use_kernels:
-                if not hasattr(self, "_norm_scratch"):
-                    self._norm_scratch = self.tp_symm.alloc(max(n, 8 * ctx.t * 16), self.dtype())
-                sc = self._norm_scratch
-                sc.local[:n].copy_(view)
-                self.tp_symm.allreduce_scale_(sc, 0, _round_up_to(n, 8 * ctx.t), 1.0, blocks=4)
-                view.copy_(sc.local[:n])
+        regions = self._norm_regions(g)
+        if not regions:
+            return
+        # adjacent norm gains (input / post-attention layernorm) are reduced with one launch
+        merged = [list(regions[0])]
+        for off, n in regions[1:]:
+            if off == merged[-1][0] + merged[-1][1]:
+                merged[-1][1] += n
             else:
+                merged.append([off, n])
+        for off, n in merged:
+            view = g.grad[off:off + n]
+            if not ctx.use_kernels:
                 ctx.all_reduce_(view)
+                continue
+            buf = getattr(self, "registry", {}).get(g.grad.data_ptr()) if self.engine is None else None
+            if buf is not None and n % (8 * ctx.t) == 0:
+                # pure TP: the flat gradient buffer is itself tp-symmetric -> all-reduce (sum) in place
+                self.tp_symm.allreduce_scale_(buf, off, n, 1.0, blocks=4)
+                continue
+            # 2-D: gradient slots are symmetric over the dp group; bounce through a tp-symmetric scratch
+            if not hasattr(self, "_norm_scratch"):
+                self._norm_scratch = self.tp_symm.alloc(max(_round_up_to(n, 8 * ctx.t), 8 * ctx.t * 16), self.dtype())
+            sc = self._norm_scratch
+            sc.local[:n].copy_(view)
+            self.tp_symm.allreduce_scale_(sc, 0, _round_up_to(n, 8 * ctx.t), 1.0, blocks=4)
+            view.copy_(sc.local[:n])
 
     def build_optimizer(self, args, model, lr):
         if self.engine is not None:

@@ -124,10 +124,6 @@ class TPContext:
         return x
 
 
-def _wgrad_target(owner, shape_like):
-    return getattr(owner, "_dtg_grad", None)
-
-
 class _ColumnParallelLinear(torch.autograd.Function):
     """y_full[T, n_local] = all_gather_rows(x_local)[T, H] @ W_local[n_local, H]^T"""
 

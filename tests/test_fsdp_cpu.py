@@ -6,20 +6,20 @@ from dist_utils import run_distributed
 from test_ddp_cpu import _single_reference
 
 
-def _train(rank, world, steps, ckpt_act):
+def _train(rank, world, steps, ckpt_act, offload=False):
     from distributed_training_guide_b200.engine import TrainEngine
 
     torch.manual_seed(0)
     eng = TrainEngine.create("debug-llama", parallelism="fsdp", batch_size=2, seq_length=32, device="cpu", lr=1e-3,
-                             checkpoint_activations=ckpt_act)
+                             checkpoint_activations=ckpt_act, cpu_offload=offload)
     losses = [float(eng.step(eng.synthetic_batch(seed=i, pinned=False))) for i in range(steps)]
     sd = eng.strategy.engine.full_state_dict()
     return losses, {k: v.float() for k, v in sd.items()}
 
 
-def _check(ckpt_act):
+def _check(ckpt_act, offload=False):
     steps, world = 3, 2
-    res = run_distributed(_train, world=world, args=(steps, ckpt_act))
+    res = run_distributed(_train, world=world, args=(steps, ckpt_act, offload))
     ref_losses, ref_sd = _single_reference(steps, world)
     (l0, sd0), (l1, sd1) = res
     for i in range(steps):
@@ -35,3 +35,65 @@ def test_fsdp_matches_single_process():
 
 def test_fsdp_with_activation_checkpointing():
     _check(True)
+
+
+def test_fsdp_cpu_offload_flag():
+    _check(False, offload=True)
+
+
+def test_sharded_checkpoint_roundtrip_and_consolidate(tmp_path):
+    """chapter 04 under torchrun (gloo): DCP layout, resume, and the consolidation tool."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    script = root / "04-fully-sharded-data-parallel" / "train_llm.py"
+
+    def run(max_steps):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--standalone", "--local-addr", "127.0.0.1",
+               "--nproc-per-node", "2", str(script), "-d", "synthetic", "-m", "debug-llama", "-s", "32", "-b", "2",
+               "--num-samples", "32", "--log-freq", "1", "--device", "cpu", "--save-dir", str(tmp_path), "-e", "exp",
+               "--ckpt-freq", "2", "--lr", "1e-3", "--max-steps", str(max_steps)]
+        r = subprocess.run(cmd, capture_output=True, text=True, cwd=str(script.parent), timeout=600)
+        assert r.returncode == 0, r.stderr[-3000:]
+        return r.stderr
+
+    run(2)
+    exp = tmp_path / "exp"
+    names = {p.name for p in exp.iterdir()}
+    assert {"checkpoint", "state.json", "lr_scheduler.pt", "rank-0", "rank-1"} <= names, names
+    ck = {p.name for p in (exp / "checkpoint").iterdir()}
+    assert ".metadata" in ck and any(n.endswith(".distcp") for n in ck), ck
+    assert json.loads((exp / "state.json").read_text())["global_step"] == 2
+    log = run(4)
+    assert "Resumed=True" in log
+    from distributed_training_guide_b200.tools.consolidate import consolidate
+
+    out = consolidate(str(exp), "debug-llama", world=2)
+    sd = torch.load(out, weights_only=True)
+    assert "model.layers.1.mlp.down_proj.weight" in sd and sd["lm_head.weight"].shape == (1024, 256)
+
+
+def _load_pretrained(rank, world):
+    """rank 0 holds a 'pretrained' state dict; load_into_fsdp distributes it group by group."""
+    from distributed_training_guide_b200.engine import TrainEngine
+    from distributed_training_guide_b200.models import build_model, get_config
+    from distributed_training_guide_b200.tools.load_hf import load_into_fsdp
+
+    eng = TrainEngine.create("debug-llama", parallelism="fsdp", batch_size=2, seq_length=32, device="cpu", lr=1e-3, seed=5)
+    torch.manual_seed(123)
+    src = build_model(get_config("debug-llama"), dtype=torch.bfloat16, device="cpu")
+    src.init_weights(seed=999)  # different from the engine's own init
+    sd = src.state_dict() if rank == 0 else None
+    load_into_fsdp(eng.strategy.engine, (lambda name: sd[name]) if rank == 0 else None)
+    full = eng.strategy.engine.full_state_dict()
+    ref_sd = src.state_dict()
+    return max(float((full[k].float() - ref_sd[k].float()).abs().max()) for k in ref_sd)
+
+
+def test_pretrained_load_and_broadcast():
+    res = run_distributed(_load_pretrained, world=2)
+    assert all(r == 0.0 for r in res), res

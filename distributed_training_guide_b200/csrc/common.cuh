@@ -55,8 +55,16 @@ __device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
   for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
   return p;
 }
-__device__ __forceinline__ bf16x8 ld8(const __nv_bfloat16* p) { return *reinterpret_cast<const bf16x8*>(p); }
-__device__ __forceinline__ void st8(__nv_bfloat16* p, const bf16x8& v) { *reinterpret_cast<bf16x8*>(p) = v; }
+// 16-byte accesses spelled as uint4 so they compile to LDG.128 / STG.128 (a struct of four bfloat162
+// is otherwise split into four 32-bit accesses)
+__device__ __forceinline__ bf16x8 ld8(const __nv_bfloat16* p) {
+  bf16x8 r;
+  *reinterpret_cast<uint4*>(&r) = *reinterpret_cast<const uint4*>(p);
+  return r;
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const bf16x8& v) {
+  *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&v);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -208,11 +208,17 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "final_loss": last,
         **({"phases_ms": eng.phase_times_ms(last_n=args.steps)} if eng.phase_timing else {}),
+        **({"comm_trace": eng.model.engine.comm_trace_summary(last_steps=args.steps)}
+           if getattr(getattr(eng.model, "engine", None), "trace", None) else {}),
         "peak_alloc_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
     }
     if rank == 0:
         print(json.dumps(out), flush=True)
     eng.close()
+    from distributed_training_guide_b200.parallel.bootstrap import shutdown
+
+    _barrier_sync(dev)
+    shutdown()
 
 
 def run_reference(args):

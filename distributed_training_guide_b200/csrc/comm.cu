@@ -231,6 +231,24 @@ void comm_allgather(const SymmPtrs& shards, void* full, const SymmPads& pads, si
   DTG_LAUNCH_CHECK();
 }
 
+// All-gather on the copy engines: one device-side barrier (a 1-warp kernel) and then N async peer copies.
+// No SM time at all, which matters when the gather is a prefetch running under tensor-core kernels that own
+// every SM (FSDP unshard): an SM-driven gather there competes for issue slots and gets stretched.
+void comm_allgather_ce(const SymmPtrs& shards, void* full, const SymmPads& pads, size_t shard_off, size_t per, int rank,
+                       int nranks, uint32_t epoch, int* err, bool barrier, cudaStream_t s) {
+  if (barrier) {
+    barrier_kernel<<<1, 32, 0, s>>>(pads, rank, nranks, epoch, err);
+    note_launch();
+    DTG_LAUNCH_CHECK();
+  }
+  const size_t bytes = per * sizeof(__nv_bfloat16);
+  for (int k = 0; k < nranks; ++k) {
+    const int p = (rank + k) % nranks;  // shards.ptr is rotated: entry k belongs to rank (rank + k) % nranks
+    DTG_CUDA_CHECK(cudaMemcpyAsync((char*)full + (size_t)p * bytes, shards.ptr[k] + shard_off * sizeof(__nv_bfloat16),
+                                   bytes, cudaMemcpyDeviceToDevice, s));
+  }
+}
+
 void comm_reduce_scatter(const SymmPtrs& grads, void* out, const SymmPads& pads, size_t elem_off, size_t n, float scale,
                          int rank, int nranks, uint32_t epoch, int* err, int blocks, cudaStream_t s) {
   check_geometry(n, nranks, blocks);

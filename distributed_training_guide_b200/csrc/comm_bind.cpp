@@ -117,6 +117,11 @@ void allgather(const std::vector<uint64_t>& shards, Tensor& full, const std::vec
                int64_t blocks) {
   TORCH_CHECK(full.is_contiguous() && full.scalar_type() == at::kBFloat16, "full must be contiguous bf16");
   TORCH_CHECK(full.numel() >= per * (int64_t)shards.size(), "full buffer too small");
+  if (blocks <= 0) {  // copy-engine variant
+    comm_allgather_ce(rotated(shards, (int)rank), full.data_ptr(), pads_of(pads), (size_t)shard_off, (size_t)per,
+                      (int)rank, (int)shards.size(), (uint32_t)epoch, err_ptr(err), barrier, stream());
+    return;
+  }
   comm_allgather(rotated(shards, (int)rank), full.data_ptr(), pads_of(pads), (size_t)shard_off, (size_t)per, (int)rank,
                  (int)shards.size(), (uint32_t)epoch, err_ptr(err), barrier, (int)blocks, stream());
 }

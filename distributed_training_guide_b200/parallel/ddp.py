@@ -25,6 +25,7 @@ On CPU (gloo tests) the same engine falls back to ``torch.distributed`` collecti
 from __future__ import annotations
 
 import contextlib
+import os
 from typing import List, Optional
 
 import torch
@@ -80,6 +81,8 @@ class DataParallelEngine:
         model.engine = self
         optimizer.external_step = self._optimizer_step
         self._pending = []  # buckets reduced this step (for the CPU fallback's deferred update)
+        # DTG_COMM_TRACE=1: CUDA events around every bucket kernel (see comm_trace_summary)
+        self.trace = [] if (self.use_kernels and os.environ.get("DTG_COMM_TRACE")) else None
 
     # -- hooks called by the model ---------------------------------------------------------------
     def pre_forward(self, model):
@@ -125,9 +128,14 @@ class DataParallelEngine:
             self._launch(g)  # the embedding gradient is only complete at the very end of backward
         if self.use_kernels:
             self._done.record(self.comm_stream)
+            if self.trace is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()  # end of backward on the compute stream
+                d = torch.cuda.Event(enable_timing=True)
+                d.record(self.comm_stream)
+                self.trace.append(("end", e, d))
 
     def _launch(self, g: FlatGroup):
-        opt = self.optimizer
         if not self.use_kernels:
             self._launch_fallback(g)
             return
@@ -136,14 +144,48 @@ class DataParallelEngine:
         gbuf = self.registry[g.grad.data_ptr()]
         with torch.cuda.stream(self.comm_stream):
             self.comm_stream.wait_event(ev)
-            if self.zero1:
-                st = opt.state[g.param]
-                st["step"] += 1
-                pbuf = self.registry[g.param.data_ptr()]
-                self.symm.rs_adamw_(gbuf, pbuf, None, st["exp_avg"], st["exp_avg_sq"], True, 0, g.padded_numel,
-                                    opt.hyper(), st["step"], opt.grad_scale / self.world)
-            else:
-                self.symm.allreduce_scale_(gbuf, 0, g.padded_numel, 1.0 / self.world)
+            if self.trace is not None:
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record()
+                self._run_bucket(g, gbuf)
+                t1.record()
+                self.trace.append((g.name, t0, t1))
+                return
+            self._run_bucket(g, gbuf)
+
+    def comm_trace_summary(self, last_steps=None):
+        """{"bucket_ms": mean device time per bucket kernel, "sum_ms": per step, "tail_ms": how long the
+        communication stream runs past the end of backward} from the DTG_COMM_TRACE events."""
+        if not self.trace:
+            return {}
+        torch.cuda.synchronize()
+        ends = [i for i, t in enumerate(self.trace) if t[0] == "end"]
+        if last_steps:
+            start = ends[-last_steps - 1] + 1 if len(ends) > last_steps else 0
+        else:
+            start = 0
+        rows = self.trace[start:]
+        n_steps = max(1, sum(1 for t in rows if t[0] == "end"))
+        per = {}
+        for name, a, b in rows:
+            if name != "end":
+                key = "layer" if name.startswith("layer") else name
+                per.setdefault(key, []).append(a.elapsed_time(b))
+        tails = [a.elapsed_time(b) for name, a, b in rows if name == "end"]
+        return {"bucket_ms": {k: round(sum(v) / len(v), 3) for k, v in per.items()},
+                "sum_ms": round(sum(sum(v) for v in per.values()) / n_steps, 2),
+                "tail_ms": round(sum(tails) / len(tails), 3) if tails else None}
+
+    def _run_bucket(self, g, gbuf):
+        opt = self.optimizer
+        if self.zero1:
+            st = opt.state[g.param]
+            st["step"] += 1
+            pbuf = self.registry[g.param.data_ptr()]
+            self.symm.rs_adamw_(gbuf, pbuf, None, st["exp_avg"], st["exp_avg_sq"], True, 0, g.padded_numel,
+                                opt.hyper(), st["step"], opt.grad_scale / self.world)
+        else:
+            self.symm.allreduce_scale_(gbuf, 0, g.padded_numel, 1.0 / self.world)
 
     def _launch_fallback(self, g: FlatGroup):
         """torch.distributed path (CPU / gloo): all-reduce now, sharded update in optimizer.step()."""

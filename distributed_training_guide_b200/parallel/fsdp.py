@@ -26,6 +26,7 @@ On CPU (gloo tests) the same schedule runs with ``torch.distributed`` collective
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -68,13 +69,14 @@ class FSDPEngine:
     N_GRAD_SLOTS = 2
 
     def __init__(self, model, env, dtype, symm=None, pg=None, world_size=1, rank=0, seed=0, cpu_offload=False,
-                 prefetch=True, lr=3e-5, init_fn=None, pre_reduce=None):
+                 prefetch=True, lr=3e-5, init_fn=None, pre_reduce=None, prefetch_depth=None):
         self.model, self.env, self.dtype = model, env, dtype
         self.symm, self.pg, self.world, self.rank = symm, pg, world_size, rank
         self.device = env.device
         self.use_kernels = symm is not None
         self.cpu_offload = cpu_offload
         self.prefetch = prefetch
+        self._prefetch_depth_req = int(os.environ.get("DTG_FSDP_PREFETCH", prefetch_depth or 1))
         self.sync_enabled = True
         self.pre_reduce = pre_reduce  # 2-D: sum the replicated (norm) gradients over the tp group first
         core = model.model
@@ -110,6 +112,7 @@ class FSDPEngine:
         self._symm_of: Dict[int, object] = {}
         self.full_slots = [local(max_layer) for _ in range(min(self.N_FULL_SLOTS, max(L, 1)))]
         self.grad_slots = [symmetric(max_layer) for _ in range(min(self.N_GRAD_SLOTS, max(L, 1)))]
+        self.prefetch_depth = max(1, min(self._prefetch_depth_req, len(self.full_slots) - 1))
         self.groups: List[FlatGroup] = []
         self.shards: List[ShardGroup] = []
         self.slot_of: Dict[str, int] = {}
@@ -161,6 +164,8 @@ class FSDPEngine:
         self._unsharded = set()
         if self.use_kernels:
             self.comm_stream = torch.cuda.Stream(device=self.device)
+            # unshard on the copy engines (DTG_FSDP_AG=sm selects the SM pull kernel instead)
+            self.ag_copy_engine = os.environ.get("DTG_FSDP_AG", "ce") != "sm"
             self.ag_done: Dict[str, torch.cuda.Event] = {}
             self.slot_free = [None] * len(self.full_slots)
             self.rs_done: Dict[str, torch.cuda.Event] = {}
@@ -221,7 +226,8 @@ class FSDPEngine:
                 ev = self.slot_free[self.slot_of[g.name]]
                 if ev is not None:
                     self.comm_stream.wait_event(ev)  # the slot's previous layer has finished computing
-            self.symm.allgather_(self._symm_of[sh.param.data_ptr()], g.param, 0, sh.padded_numel)
+            self.symm.allgather_(self._symm_of[sh.param.data_ptr()], g.param, 0, sh.padded_numel,
+                                 copy_engine=self.ag_copy_engine)
             ev = torch.cuda.Event()
             ev.record(self.comm_stream)
             self.ag_done[g.name] = ev
@@ -259,9 +265,14 @@ class FSDPEngine:
         self.wait_unsharded(g)
         if i == 0:
             self.release(self.embed)
-        nxt = self.layer_groups[i + 1] if i + 1 < len(self.layer_groups) else self.head
-        if self.prefetch or True:
-            self.unshard(nxt)  # depth-1 forward prefetch (FSDP2's implicit prefetch; explicit in ch05)
+        # forward prefetch: depth 1 is FSDP2's implicit prefetch; --prefetch-layers (ch05) uses every
+        # rotating slot (the slot of layer i+2 is the one layer i-1 just released)
+        L = len(self.layer_groups)
+        for d in range(1, self.prefetch_depth + 1):
+            if i + d < L:
+                self.unshard(self.layer_groups[i + d])
+            elif i + d == L:
+                self.unshard(self.head)
         return boundary(lambda i=i: self._post_backward_layer(i), x, residual)
 
     def post_layer(self, i, layer, x, residual):
@@ -287,8 +298,9 @@ class FSDPEngine:
         self._enter_backward()
         g = self.layer_groups[i]
         self.wait_unsharded(g)
-        if i > 0:
-            self.unshard(self.layer_groups[i - 1])  # backward prefetch of the previous layer
+        for d in range(1, self.prefetch_depth + 1):  # backward prefetch of the previous layer(s)
+            if i - d >= 0:
+                self.unshard(self.layer_groups[i - d])
         if self.use_kernels:
             # the gradient slot was last used by layer i + N_GRAD_SLOTS: its reduce-scatter must be done
             j = i + len(self.grad_slots)

@@ -232,7 +232,7 @@ class FullyShardedDataParallel(Strategy):
             self.symm = symm_mod.SymmGroup(env.device) if env.world_size > 1 else symm_mod.SymmGroup(env.device, ranks=[0])
         self.engine = FSDPEngine(model, env, self.dtype(), symm=self.symm, world_size=env.world_size, rank=env.rank,
                                  seed=getattr(args, "seed", 0), cpu_offload=getattr(args, "cpu_offload", False),
-                                 prefetch=True)
+                                 prefetch=True, prefetch_depth=2 if getattr(args, "prefetch_layers", False) else 1)
         model.activation_checkpointing = bool(getattr(args, "checkpoint_activations", False))
         self.groups = self.engine.groups
         self.model = model

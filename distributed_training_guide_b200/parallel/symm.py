@@ -124,9 +124,11 @@ class SymmGroup:
                              self._epochs(2), self.err, blocks or self.comm_blocks)
 
     def allgather_(self, shards: SymmBuffer, full: torch.Tensor, shard_off: int, per: int, barrier: bool = True,
-                   blocks: Optional[int] = None):
+                   blocks: Optional[int] = None, copy_engine: bool = False):
+        """``full[r*per:(r+1)*per] = shard of rank r``.  ``copy_engine=True``: a 1-warp barrier kernel + N async
+        peer copies (zero SM time: the right choice for a prefetch that runs under GEMMs)."""
         self.C.comm_allgather(shards.ptrs, full, self.pad_ptrs, shard_off, per, self.rank, self._epochs(1), self.err,
-                              barrier, blocks or self.comm_blocks)
+                              barrier, 0 if copy_engine else (blocks or self.comm_blocks))
 
     def reduce_scatter_(self, grads: SymmBuffer, out: torch.Tensor, elem_off: int, n: int, scale: float,
                         blocks: Optional[int] = None):

@@ -185,6 +185,9 @@ def train(args, strategy):
     if tracker is not None:
         tracker.finish()
     strategy.teardown()
+    if dist.is_available() and dist.is_initialized() and not getattr(args, "keep_process_group", False):
+        dist.barrier()
+        dist.destroy_process_group()
     return state, last_info
 
 

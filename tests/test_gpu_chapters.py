@@ -35,7 +35,7 @@ def test_chapter01_on_gpu(tmp_path, model, seq):
     assert json.loads((tmp_path / "exp" / "state.json").read_text())["global_step"] == 3
     recs2, log = _run(script, common + ["--max-steps", "6"])
     assert "Resumed=True" in log and recs2[-1]["global_step"] == 6
-    assert recs2[-1]["running_loss"] < recs[0]["running_loss"]
+    assert all(0 < r["running_loss"] < 20 for r in recs + recs2)  # random tokens: finite, near ln(V)
 
 
 @pytest.mark.multigpu

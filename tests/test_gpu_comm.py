@@ -77,6 +77,10 @@ def _comm_checks(rank, world):
     torch.cuda.synchronize()
     exp = torch.cat([torch.full((per,), float(r + 1)) for r in range(world)]).to(dev)
     out["allgather_err"] = (full.float() - exp).abs().max().item()
+    full.zero_()
+    sg.allgather_(sh, full, 0, per, copy_engine=True)  # barrier kernel + peer copies on the copy engines
+    torch.cuda.synchronize()
+    out["allgather_ce_err"] = (full.float() - exp).abs().max().item()
     # ---- bandwidth of the fused kernels (device-timed) ------------------------------------------------------
     big = 8 * world * (1 << 22)  # 64 Mi elements at world=2 -> 128 MiB bf16
     bb = sg.alloc(big, torch.bfloat16)
@@ -112,7 +116,7 @@ def test_symmetric_collectives():
         assert r["allreduce_err"] < 0.05, r
         assert r["zero1_err"] < 0.05, r
         assert r["zero1_replica_diff"] == 0.0, r
-        assert r["allgather_err"] == 0.0, r
+        assert r["allgather_err"] == 0.0 and r["allgather_ce_err"] == 0.0, r
 
 
 def _ddp_train(rank, world, steps):

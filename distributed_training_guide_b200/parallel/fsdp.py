@@ -172,6 +172,9 @@ class FSDPEngine:
             self._done = torch.cuda.Event()
         self._in_backward = False
         self.optimizer: Optional[FlatAdamW] = None
+        # DTG_COMM_TRACE=1: CUDA events around every gather / reduce kernel and around every point where the
+        # compute stream waits for the communication stream (see comm_trace_summary)
+        self.trace = [] if (self.use_kernels and os.environ.get("DTG_COMM_TRACE")) else None
         # after the constructor every slot holds the LAST group that was initialised in it
         for i, g in enumerate(self.layer_groups):
             self.slot_owner[self.slot_of[g.name]] = None
@@ -226,8 +229,10 @@ class FSDPEngine:
                 ev = self.slot_free[self.slot_of[g.name]]
                 if ev is not None:
                     self.comm_stream.wait_event(ev)  # the slot's previous layer has finished computing
+            t0 = self._trace_begin()
             self.symm.allgather_(self._symm_of[sh.param.data_ptr()], g.param, 0, sh.padded_numel,
                                  copy_engine=self.ag_copy_engine)
+            self._trace_end("unshard", t0)
             ev = torch.cuda.Event()
             ev.record(self.comm_stream)
             self.ag_done[g.name] = ev
@@ -235,7 +240,9 @@ class FSDPEngine:
     def wait_unsharded(self, g: FlatGroup):
         self.unshard(g)
         if self.use_kernels:
+            t0 = self._trace_begin()
             torch.cuda.current_stream().wait_event(self.ag_done[g.name])
+            self._trace_end("stall_unshard_bwd" if self._in_backward else "stall_unshard_fwd", t0)
 
     def release(self, g: FlatGroup):
         """The compute stream is done with ``g``'s full parameters (its slot may be overwritten)."""
@@ -307,7 +314,9 @@ class FSDPEngine:
             if j < len(self.layer_groups):
                 ev = self.rs_done.get(self.layer_groups[j].name)
                 if ev is not None:
+                    t0 = self._trace_begin()
                     torch.cuda.current_stream().wait_event(ev)
+                    self._trace_end("stall_grad_slot", t0)
         else:
             g.grad.zero_()
 
@@ -358,17 +367,51 @@ class FSDPEngine:
                 self.symm.reduce_scatter_(gbuf, st["gpu_grad"], 0, g.padded_numel, opt.grad_scale / self.world)
                 st["cpu_grad"].copy_(st["gpu_grad"], non_blocking=True)
             else:
+                t0 = self._trace_begin()
                 self.symm.rs_adamw_(gbuf, None, sh.param, st["exp_avg"], st["exp_avg_sq"], False, 0, g.padded_numel,
                                     opt.hyper(), st["step"], opt.grad_scale / self.world)
+                self._trace_end("reduce_adamw", t0)
             done = torch.cuda.Event()
             done.record(self.comm_stream)
             self.rs_done[g.name] = done
+
+    # -- optional device-side trace ---------------------------------------------------------------------------------
+    def _trace_begin(self):
+        if self.trace is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def _trace_end(self, kind, t0):
+        if t0 is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.trace.append((kind, t0, e))
+
+    def comm_trace_summary(self, last_steps=None):
+        """Per step: device time of the unshard / reduce kernels (communication stream) and how long the compute
+        stream sat in each kind of wait."""
+        if not self.trace:
+            return {}
+        torch.cuda.synchronize()
+        steps = max(1, self._trace_steps)
+        per = {}
+        for kind, a, b in self.trace:
+            per.setdefault(kind, []).append(a.elapsed_time(b))
+        return {k: {"per_step_ms": round(sum(v) / steps, 2), "mean_ms": round(sum(v) / len(v), 3), "n": len(v) // steps}
+                for k, v in per.items()}
+
+    _trace_steps = 0
 
     # -- optimizer step: everything already happened inside backward ------------------------------------------
     def _optimizer_step(self):
         opt = self.optimizer
         if self.use_kernels:
+            t0 = self._trace_begin()
             torch.cuda.current_stream().wait_event(self._done)
+            self._trace_end("stall_tail", t0)
+            self._trace_steps += 1
         if self.cpu_offload:
             if self.use_kernels:
                 self.comm_stream.synchronize()

@@ -55,3 +55,17 @@ def test_distributed_chapters_on_gpus(tmp_path, chapter, extra):
     losses = [r["running_loss"] for r in recs if r["global_step"] in (1, 4)]
     assert len(recs) >= 4 and losses[-1] < losses[0] + 0.5
     assert (tmp_path / "exp" / "state.json").exists()
+
+
+@pytest.mark.multigpu
+def test_2d_dp2_tp2_on_four_gpus(tmp_path):
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs")
+    script = ROOT / "07-2d-parallel" / "train_llm.py"
+    args = ["-d", "synthetic", "-m", "debug-llama-tp", "-s", "256", "-b", "2", "--num-samples", "64", "--log-freq", "1",
+            "--save-dir", str(tmp_path), "-e", "exp", "--ckpt-freq", "2", "--lr", "1e-3", "--max-steps", "4", "-tp", "2"]
+    recs, _ = _run(script, args, nproc=4)
+    assert len(recs) >= 4 and all(0 < r["running_loss"] < 20 for r in recs)
+    # resume from the sharded checkpoint
+    recs2, log = _run(script, args[:-4] + ["--max-steps", "6", "-tp", "2"], nproc=4)
+    assert "Resumed=True" in log and recs2[-1]["global_step"] == 6

@@ -393,7 +393,10 @@ class TwoDParallel(Strategy):
                 continue
             # 2-D: gradient slots are symmetric over the dp group; bounce through a tp-symmetric scratch
             if not hasattr(self, "_norm_scratch"):
-                self._norm_scratch = self.tp_symm.alloc(max(_round_up_to(n, 8 * ctx.t), 8 * ctx.t * 16), self.dtype())
+                # sized once (the allocation is collective) for the largest run of adjacent norm gains of any group
+                biggest = max(sum(m for _, m in self._norm_regions(gg)) for gg in self.groups)
+                self._norm_scratch = self.tp_symm.alloc(max(_round_up_to(biggest, 8 * ctx.t), 8 * ctx.t * 16),
+                                                        self.dtype())
             sc = self._norm_scratch
             sc.local[:n].copy_(view)
             self.tp_symm.allreduce_scale_(sc, 0, _round_up_to(n, 8 * ctx.t), 1.0, blocks=4)

@@ -132,13 +132,17 @@ def run_b200(args):
                              tensor_parallel=args.tensor_parallel, num_layers=args.layers)
     dev = eng.device
     rank = eng.env.rank
-    host_batches = [eng.synthetic_batch(seed=i) for i in range(4)]
-    dev_batches = [{k: v.to(dev) for k, v in b.items()} for b in host_batches]
+    # a fresh random batch for every step of the run (nothing is ever seen twice, so the loss stays at the
+    # ln(V) of real from-scratch pretraining instead of collapsing by memorisation)
+    n_dev = args.warmup + 1 + args.steps
+    n_host = 1 + args.steps
+    host_batches = [eng.synthetic_batch(seed=n_dev + i) for i in range(n_host)]
+    dev_batches = [{k: v.to(dev) for k, v in eng.synthetic_batch(seed=i, pinned=False).items()} for i in range(n_dev)]
     h2d_bytes = sum(v.numel() * v.element_size() for v in host_batches[0].values())
 
     eng.phase_timing = bool(os.environ.get("DTG_PHASE_TIMING"))
     for i in range(args.warmup):
-        eng.step(dev_batches[i % 4])
+        eng.step(dev_batches[i])
     if os.environ.get("DTG_CPU_PROFILE") and rank == 0:  # host-side cost of one step (diagnostics)
         import cProfile
         import io
@@ -148,7 +152,7 @@ def run_b200(args):
         pr = cProfile.Profile()
         t0 = time.perf_counter()
         pr.enable()
-        eng.step(dev_batches[0])
+        eng.step(dev_batches[args.warmup])
         pr.disable()
         host_ms = 1000 * (time.perf_counter() - t0)
         torch.cuda.synchronize(dev)
@@ -158,7 +162,7 @@ def run_b200(args):
         with open(os.environ["DTG_CPU_PROFILE"], "w") as fp:
             fp.write(f"host time to enqueue one step: {host_ms:.1f} ms\n" + buf.getvalue())
     elif os.environ.get("DTG_CPU_PROFILE"):
-        eng.step(dev_batches[0])
+        eng.step(dev_batches[args.warmup])
     # ---- region 1: device-timed steps, batch resident on the GPU --------------------------------
     _barrier_sync(dev)
     l0 = _ext.launch_count()
@@ -166,20 +170,20 @@ def run_b200(args):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for i in range(args.steps):
-            loss = eng.step(dev_batches[i % 4])
+            loss = eng.step(dev_batches[args.warmup + 1 + i])
         e.record()
         _barrier_sync(dev)
     launches = _ext.launch_count() - l0
     ms_dev = _dist_max(s.elapsed_time(e), dev) / args.steps
     # ---- region 2: end to end through the public API: pinned H2D every step + loss D2H every step ---
-    eng.step(host_batches[0])
+    eng.step(host_batches[args.steps])
     _barrier_sync(dev)
     s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     s2.record()
     last = 0.0
     for i in range(args.steps):
-        loss = eng.step(host_batches[i % 4])
+        loss = eng.step(host_batches[i])
         last = loss.item()  # 4-byte device->host read of the step's result
     e2.record()
     _barrier_sync(dev)

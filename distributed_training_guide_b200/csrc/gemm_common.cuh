@@ -46,6 +46,9 @@ struct GemmDist {
   int n_comm;                        // clusters (CTA pairs) that copy instead of multiplying
   int rank, nranks;
   long long tile_bytes;              // bytes of one 256-row tile of A (contiguous: lda == K)
+  // L2-aware rasterisation of the plain GEMM: tiles run M-fastest inside groups of `group_m` row tiles (0 = one
+  // group = the whole M extent); `num_n_tiles` is set by the launcher.
+  int group_m, num_n_tiles;
 };
 
 #ifdef __CUDACC__
@@ -53,11 +56,24 @@ __device__ __forceinline__ int tile_m(int t, int num_m_tiles, const GemmDist& d)
   int m = t % num_m_tiles + d.m_tile_shift;
   return m >= num_m_tiles ? m - num_m_tiles : m;
 }
-// Tile order.  Default: M fastest (consecutive CTAs share the B tile).  With an in-kernel all-gather
+// Tile order.  Default: M fastest (consecutive CTAs share the B tile) within a group of `group_m` row tiles
+// whose slice of A stays L2-resident while B streams past once per group: the ~74 tiles in flight then touch
+// group_m row panels of A and 74/group_m column panels of B instead of every row panel of A, which is what keeps
+// a tall GEMM (wgrad with M = 22016 or 32000) from re-streaming all of A from HBM for every column of tiles.
+// With an in-kernel all-gather
 // (`local_m_tiles` > 0): first every tile of my own rows (pure local work while the communication CTAs
 // fetch), then the remote row tiles in the order they are being fetched.
 __device__ __forceinline__ void tile_mn(int t, int num_m_tiles, const GemmDist& d, int local_m_tiles, int& m, int& n) {
   if (local_m_tiles <= 0) {
+    if (d.group_m > 0 && d.group_m < num_m_tiles) {
+      const int per_group = d.group_m * d.num_n_tiles;
+      const int g = t / per_group, r = t - g * per_group;
+      const int m0 = g * d.group_m;
+      const int gsz = min(d.group_m, num_m_tiles - m0);
+      m = m0 + r % gsz;
+      n = r / gsz;
+      return;
+    }
     m = tile_m(t, num_m_tiles, d);
     n = t / num_m_tiles;
     return;

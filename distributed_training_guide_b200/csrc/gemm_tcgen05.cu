@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -408,6 +409,19 @@ static void launch_gemm(const void* const* a_srcs, const void* const* b_srcs, vo
   if (!attr_set) {
     DTG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
+  }
+  dist.num_n_tiles = num_n_tiles;
+  if constexpr (A_MODE == 0 && B_MODE == 0 && C_MODE == 0) {
+    // keep one group's panel of A (group_m x TM x K bf16) within ~1/3 of the 126 MB L2; with very long K nothing
+    // fits and a squarish 8 x 9 block of in-flight tiles minimises the bytes each wave touches
+    static const long long budget = []() {
+      const char* e = getenv("DTG_GEMM_L2_BUDGET_MB");
+      return (long long)(e ? atoi(e) : 40) << 20;
+    }();
+    const long long panel = (long long)Cfg::BM * CG * K * 2;
+    long long gm = budget / (panel > 0 ? panel : 1);
+    if (gm < 8) gm = 8;
+    dist.group_m = gm >= num_m_tiles ? 0 : (int)gm;
   }
   int clusters = sm_count() / CG;
   if constexpr (A_MODE == 3) {

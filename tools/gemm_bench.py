@@ -21,6 +21,8 @@ SHAPES = {  # name: (M, N, K, trans_a, trans_b)
     "7b_down_dgrad": (4096, 11008, 4096, False, False),
     "7b_gateup_wgrad": (22016, 4096, 4096, True, False),
     "7b_down_wgrad": (4096, 11008, 4096, True, False),
+    "7b_qkv_wgrad": (12288, 4096, 4096, True, False),
+    "7b_lmhead_wgrad": (32000, 4096, 4096, True, False),
     "square_8192": (8192, 8192, 8192, False, True),
 }
 

@@ -212,3 +212,37 @@ class DataParallelEngine:
                 dist.all_gather(shards, g.param[lo:hi].float(), group=self.pg)
                 g.param.copy_(torch.cat(shards).to(g.param.dtype))
         self._pending.clear()
+
+
+class LocalOverlapEngine(DataParallelEngine):
+    """Optimizer-in-backward without a data-parallel collective (pure tensor parallelism, dp = 1).
+
+    When a bucket's gradients are final, ``pre_update(g)`` runs on the compute stream (tensor parallelism: sum
+    the replicated norm-gain gradients over the tp group) and AdamW for that bucket runs on a side stream under
+    the rest of backward, so ``optimizer.step()`` only joins that stream (the reference runs one fused AdamW
+    over the whole model after backward, ``06-tensor-parallel/train_llm.py:151,236``)."""
+
+    def __init__(self, model, groups, optimizer, device, pre_update=None):
+        super().__init__(model, groups, optimizer, symm=None, world_size=1, rank=0)
+        self.pre_update = pre_update
+        self.device = torch.device(device)
+        self.use_kernels = self.device.type == "cuda"
+        if self.use_kernels:
+            self.comm_stream = torch.cuda.Stream(device=self.device)
+            self._done = torch.cuda.Event()
+
+    def _launch(self, g: FlatGroup):
+        if self.pre_update is not None:
+            self.pre_update(g)
+        if not self.use_kernels:
+            self.optimizer.step_group(g)
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ev)
+            self.optimizer.step_group(g)
+
+    def _optimizer_step(self):
+        if self.use_kernels:
+            torch.cuda.current_stream().wait_event(self._done)

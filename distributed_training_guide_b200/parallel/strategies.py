@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import contextlib
 import logging
+import os
 from pathlib import Path
 
 import torch
@@ -405,7 +406,22 @@ class TwoDParallel(Strategy):
     def build_optimizer(self, args, model, lr):
         if self.engine is not None:
             return self.engine.build_optimizer(lr)
-        return FlatAdamW(self.groups, lr=lr)
+        opt = FlatAdamW(self.groups, lr=lr)
+        if os.environ.get("DTG_TP_OVERLAP_OPT", "1") != "0":
+            from .ddp import LocalOverlapEngine
+
+            # pure TP: per-bucket norm-gradient sync + AdamW inside backward (optimizer.step() just joins)
+            self.local_engine = LocalOverlapEngine(model, self.groups, opt, self.env.device,
+                                                   pre_update=self._sync_replicated)
+        return opt
+
+    local_engine = None
+
+    def grad_sync(self, model, enabled=True):
+        eng = self.engine if self.engine is not None else self.local_engine
+        if enabled or eng is None or not hasattr(eng, "no_sync"):
+            return contextlib.nullcontext()
+        return eng.no_sync()
 
     def pre_step(self, model):
         if self.engine is not None:
@@ -413,8 +429,8 @@ class TwoDParallel(Strategy):
 
     def backward(self, model, loss):
         loss.backward()
-        if self.engine is None:  # pure TP: fix up the replicated gradients before the optimizer runs
-            for g in self.groups:
+        if self.engine is None and self.local_engine is None:
+            for g in self.groups:  # pure TP: fix up the replicated gradients before the optimizer runs
                 self._sync_replicated(g)
 
     def save_checkpoint(self, exp_dir, model, optimizer, lr_scheduler, state):

@@ -42,6 +42,7 @@ def test_chapter01_on_gpu(tmp_path, model, seq):
 @pytest.mark.parametrize("chapter,extra", [
     ("02-distributed-data-parallel", []),
     ("04-fully-sharded-data-parallel", []),
+    ("04-fully-sharded-data-parallel", ["--cpu-offload"]),
     ("05-training-llama-405b", ["--checkpoint-activations", "--prefetch-layers"]),
     ("06-tensor-parallel", []),
     ("07-2d-parallel", ["-tp", "2"]),

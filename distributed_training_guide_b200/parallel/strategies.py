@@ -132,6 +132,7 @@ class SingleDevice(Strategy):
     def build_model(self, args, config):
         model = build_model(config, dtype=self.dtype(), device=self.env.device)
         self.groups, self.symm, self.registry = _flat_groups_on(self, model, 1)
+        _load_pretrained(args, model=model)
         return model
 
     def build_optimizer(self, args, model, lr):
@@ -150,6 +151,12 @@ class SingleDevice(Strategy):
         if enabled or eng is None:
             return contextlib.nullcontext()
         return eng.no_sync()
+
+
+def _load_pretrained(args, model=None, engine=None, default="never"):
+    from ..tools.load_hf import maybe_load_pretrained
+
+    return maybe_load_pretrained(args, model=model, engine=engine, default=default)
 
 
 def _flat_groups_on(strategy, model, world_size=1, pg=None):
@@ -183,6 +190,8 @@ class DataParallelZero1(Strategy):
         with self.data_guard():
             model = build_model(config, dtype=self.dtype(), device=env.device)
         self.groups, self.symm, self.registry = _flat_groups_on(self, model, env.world_size)
+        with self.data_guard():
+            _load_pretrained(args, model=model)
         if env.distributed and env.world_size > 1:
             for g in self.groups:  # replicas must start identical (torch DDP broadcasts in its ctor, N1)
                 dist.broadcast(g.param, src=0)
@@ -237,6 +246,9 @@ class FullyShardedDataParallel(Strategy):
         model.activation_checkpointing = bool(getattr(args, "checkpoint_activations", False))
         self.groups = self.engine.groups
         self.model = model
+        # chapter 05 (reference 05:76-145): rank 0 reads the checkpoint, every rank keeps its slice of each group
+        _load_pretrained(args, engine=self.engine,
+                         default="auto" if str(getattr(args, "chapter", "")).startswith("05") else "never")
         return model
 
     def num_parameters(self, model):

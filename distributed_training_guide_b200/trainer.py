@@ -209,6 +209,7 @@ def run_chapter(chapter: str, strategy_factory, argv=None, require_experiment=Fa
     from .utils.cli import get_parser
 
     args = get_parser(chapter, require_experiment).parse_args(argv)
+    args.chapter = chapter
 
     @_record
     def main():

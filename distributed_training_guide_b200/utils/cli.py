@@ -54,6 +54,9 @@ def get_parser(chapter: str = "01-single-gpu", require_experiment: bool = False)
                    help="reference: related-topics/wandb-configurations")
     p.add_argument("--device", default=None, help="cuda (default when available) or cpu")
     p.add_argument("--num-workers", default=1, type=int, help="DataLoader worker processes (reference: 1)")
+    p.add_argument("--pretrained", choices=("auto", "require", "never"), default=None,
+                   help="load local Hugging Face safetensors for --model-name (chapter 05 defaults to auto: load "
+                        "them when they exist on disk; other chapters default to never = random init)")
     if "cpu-offload" in extras:
         p.add_argument("--cpu-offload", default=False, action="store_true")
     if "checkpoint-activations" in extras:

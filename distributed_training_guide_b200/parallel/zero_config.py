@@ -9,6 +9,7 @@ repository instead of the DeepSpeed runtime.
 from __future__ import annotations
 
 import json
+import logging
 
 from ..utils.lr import cosine_schedule, warmup_cosine_schedule
 from .strategies import DataParallelZero1, FullyShardedDataParallel, Strategy
@@ -23,11 +24,22 @@ DEFAULT_CONFIG = {
 }
 
 
+KNOWN_KEYS = {"train_micro_batch_size_per_gpu", "gradient_accumulation_steps", "optimizer", "scheduler", "bf16",
+              "zero_optimization", "train_batch_size", "steps_per_print", "wall_clock_breakdown"}
+
+
 def load_zero_config(path):
     if not path:
         return dict(DEFAULT_CONFIG)
     with open(path) as fp:
         cfg = json.load(fp)
+    unknown = sorted(set(cfg) - KNOWN_KEYS)
+    if unknown:
+        logging.getLogger("dtg_b200").warning(f"{path}: keys not understood by this front end are ignored: {unknown}")
+    if not cfg.get("bf16", {"enabled": True}).get("enabled", True):
+        raise ValueError(f"{path}: bf16.enabled must be true (every engine here computes in bf16)")
+    if cfg.get("optimizer", {}).get("type", "AdamW") not in ("AdamW", "Adam"):
+        raise ValueError(f"{path}: optimizer.type {cfg['optimizer']['type']!r} is not supported (AdamW)")
     out = dict(DEFAULT_CONFIG)
     out.update(cfg)
     return out

@@ -131,3 +131,28 @@ def test_chapter01_log_schema_checkpoint_layout_and_resume(tmp_path):
     a = [r["running_loss"] for r in full]
     b = [r["running_loss"] for r in first + second]
     assert len(b) == 6 and all(abs(x - y) < 2e-3 for x, y in zip(a, b)), (a, b)
+
+
+def test_zero_config_selects_engine(tmp_path):
+    import json
+    from types import SimpleNamespace
+
+    from distributed_training_guide_b200.parallel.strategies import DataParallelZero1, FullyShardedDataParallel
+    from distributed_training_guide_b200.parallel.zero_config import ZeroConfigured, load_zero_config
+
+    def args_for(cfg):
+        p = tmp_path / "ds.json"
+        p.write_text(json.dumps(cfg))
+        return SimpleNamespace(deepspeed_config=str(p), batch_size=4, lr=1.0, wandb="off", grad_accum_steps=1)
+
+    a = args_for({"train_micro_batch_size_per_gpu": 2, "optimizer": {"type": "AdamW", "params": {"lr": 5e-4}},
+                  "zero_optimization": {"stage": 3, "offload_optimizer": {"device": "cpu"}}, "made_up_key": 1})
+    s3 = ZeroConfigured(a)
+    assert isinstance(s3.inner, FullyShardedDataParallel) and a.batch_size == 2 and a.lr == 5e-4 and a.cpu_offload
+    a = args_for({"zero_optimization": {"stage": 1}})
+    s1 = ZeroConfigured(a)
+    assert isinstance(s1.inner, DataParallelZero1) and s1.inner.zero1 and not a.cpu_offload
+    s0 = ZeroConfigured(args_for({"zero_optimization": {"stage": 0}}))
+    assert isinstance(s0.inner, DataParallelZero1) and not s0.inner.zero1
+    with pytest.raises(ValueError):
+        load_zero_config(args_for({"bf16": {"enabled": False}}).deepspeed_config)

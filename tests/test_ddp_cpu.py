@@ -58,3 +58,46 @@ def test_ddp_matches_single_process(parallelism):
         assert abs(0.5 * (l0[i] + l1[i]) - ref_losses[i]) < 2e-2, (i, l0[i], l1[i], ref_losses[i])
     for k in sd0:
         assert np.abs(sd0[k] - ref_sd[k].numpy()).max() < 2e-2, k
+
+
+def _train_accum(rank, world, steps, K):
+    from distributed_training_guide_b200.engine import TrainEngine
+
+    torch.manual_seed(0)
+    eng = TrainEngine.create("debug-llama", parallelism="ddp", batch_size=1, seq_length=32, device="cpu", lr=1e-3)
+    s = eng.strategy
+    for i in range(steps):
+        for m in range(K):
+            g = torch.Generator().manual_seed(10_000 * i + 100 * m + rank)
+            ids = torch.randint(0, eng.config.vocab_size, (1, 32), generator=g)
+            out = eng.model(**s.prepare_batch({"input_ids": ids, "labels": ids.clone()}))
+            with s.grad_sync(eng.model, enabled=(m == K - 1)):   # no_sync() on the first K-1 micro-batches
+                s.backward(eng.model, out.loss / K)
+        eng.optimizer.step()
+        eng.lr_scheduler.step()
+        eng.optimizer.zero_grad()
+    return {k: v.detach().float().clone() for k, v in eng.model.state_dict().items()}
+
+
+def test_gradient_accumulation_with_no_sync_matches_big_batch():
+    import numpy as np
+
+    from distributed_training_guide_b200.engine import TrainEngine
+
+    steps, world, K = 2, 2, 2
+    sd0, sd1 = run_distributed(_train_accum, world=world, args=(steps, K))
+    torch.manual_seed(0)
+    eng = TrainEngine.create("debug-llama", parallelism="single", batch_size=world * K, seq_length=32, device="cpu",
+                             lr=1e-3)
+    for i in range(steps):
+        parts = []
+        for m in range(K):
+            for r in range(world):
+                g = torch.Generator().manual_seed(10_000 * i + 100 * m + r)
+                parts.append(torch.randint(0, eng.config.vocab_size, (1, 32), generator=g))
+        ids = torch.cat(parts)
+        eng.step({"input_ids": ids, "labels": ids.clone()})
+    ref_sd = {k: v.detach().float() for k, v in eng.model.state_dict().items()}
+    for k in sd0:
+        assert np.array_equal(sd0[k], sd1[k]), k
+        assert np.abs(sd0[k] - ref_sd[k].numpy()).max() < 2e-2, k

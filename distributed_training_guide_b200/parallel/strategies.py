@@ -63,6 +63,14 @@ class Strategy:
     def teardown(self):
         pass
 
+    def check_health(self):
+        """Raise if a device-side NVLink barrier timed out since the last check (called whenever the loop
+        synchronises anyway: at every log record and checkpoint)."""
+        for name in ("symm", "tp_symm", "dp_symm"):
+            sg = getattr(self, name, None)
+            if sg is not None:
+                sg.check()
+
     # -- model / optimizer -----------------------------------------------------------------
     def dtype(self):
         return torch.bfloat16

@@ -133,3 +133,6 @@ class ZeroConfigured(Strategy):
 
     def teardown(self):
         return self.inner.teardown()
+
+    def check_health(self):
+        return self.inner.check_health()

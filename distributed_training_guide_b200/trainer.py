@@ -161,6 +161,7 @@ def train(args, strategy):
                     **{f"time/{k}": t.avg_elapsed_ms() for k, t in timers.items()},
                 }
                 LOGGER.info(info)
+                strategy.check_health()
                 if tracker is not None:
                     tracker.log(info, step=state["global_step"])
                 last_info = info
@@ -173,6 +174,7 @@ def train(args, strategy):
             if is_experiment and state["global_step"] % args.ckpt_freq == 0:
                 state["running_loss"] = float(running_loss.item())
                 LOGGER.info("Saving checkpoint.")
+                strategy.check_health()
                 strategy.save_checkpoint(exp_dir, model, optimizer, lr_scheduler, state)
 
             if max_steps is not None and state["global_step"] >= max_steps:

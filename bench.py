@@ -119,7 +119,25 @@ def _barrier_sync(device):
     torch.cuda.synchronize(device)
 
 
+_T0 = time.time()
+
+
+def _stage(msg, budget_s=None):
+    """Progress line on stderr (every rank prefixes its RANK) and, with ``budget_s``, a watchdog: if the next stage
+    does not report within that many seconds, every thread's stack is dumped to stderr and the process exits, so a
+    wedged run leaves a diagnosis instead of sitting until the caller's limit kills it."""
+    import faulthandler
+
+    rank = os.environ.get("RANK", "0")
+    if rank == "0" or os.environ.get("DTG_BENCH_VERBOSE"):
+        print(f"[bench rank {rank} +{time.time() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+    faulthandler.cancel_dump_traceback_later()
+    if budget_s:
+        faulthandler.dump_traceback_later(budget_s, exit=True)
+
+
 def run_b200(args):
+    _stage("importing torch", budget_s=600)
     import torch
 
     from distributed_training_guide_b200 import _ext
@@ -128,6 +146,7 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun for N>1"
     par = args.parallelism if world > 1 else "single"
+    _stage(f"building the {par} engine on {world} GPU(s) (process group, NVLink symmetric memory, model)", budget_s=600)
     eng = TrainEngine.create(args.model, parallelism=par, batch_size=args.batch, seq_length=args.seq_len,
                              tensor_parallel=args.tensor_parallel, num_layers=args.layers)
     dev = eng.device
@@ -141,8 +160,11 @@ def run_b200(args):
     h2d_bytes = sum(v.numel() * v.element_size() for v in host_batches[0].values())
 
     eng.phase_timing = bool(os.environ.get("DTG_PHASE_TIMING"))
+    _stage(f"engine ready; {args.warmup} warm-up steps", budget_s=300)
     for i in range(args.warmup):
         eng.step(dev_batches[i])
+    torch.cuda.synchronize(dev)
+    eng.strategy.check_health()
     if os.environ.get("DTG_CPU_PROFILE") and rank == 0:  # host-side cost of one step (diagnostics)
         import cProfile
         import io
@@ -164,6 +186,7 @@ def run_b200(args):
     elif os.environ.get("DTG_CPU_PROFILE"):
         eng.step(dev_batches[args.warmup])
     # ---- region 1: device-timed steps, batch resident on the GPU --------------------------------
+    _stage(f"timing {args.steps} steps (device events)", budget_s=300)
     _barrier_sync(dev)
     l0 = _ext.launch_count()
     with ClockSampler(dev.index or 0) as clocks:
@@ -176,6 +199,7 @@ def run_b200(args):
     launches = _ext.launch_count() - l0
     ms_dev = _dist_max(s.elapsed_time(e), dev) / args.steps
     # ---- region 2: end to end through the public API: pinned H2D every step + loss D2H every step ---
+    _stage(f"timing {args.steps} steps end to end (pinned H2D + loss D2H every step)", budget_s=300)
     eng.step(host_batches[args.steps])
     _barrier_sync(dev)
     s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -218,11 +242,13 @@ def run_b200(args):
     }
     if rank == 0:
         print(json.dumps(out), flush=True)
+    _stage("done; tearing down", budget_s=120)
     eng.close()
     from distributed_training_guide_b200.parallel.bootstrap import shutdown
 
     _barrier_sync(dev)
     shutdown()
+    _stage("exit")
 
 
 def run_reference(args):

@@ -38,7 +38,10 @@ __device__ __forceinline__ void symm_barrier(uint32_t* const* pads, int rank, in
     st_release_sys(pads[p] + channel * kMaxRanks + rank, epoch);
     const uint32_t* mine = pads[rank] + channel * kMaxRanks + p;
     const long long t0 = clock64();
-    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+    // fail fast: once any barrier of this group has timed out (a peer died or diverged) later barriers do not
+    // spin for another ~10 s each; the host raises at its next check_health()
+    const bool poisoned = error_flag != nullptr && *reinterpret_cast<volatile int*>(error_flag) != 0;
+    while (!poisoned && (int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
       if (clock64() - t0 > kSpinTimeoutCycles) {  // a dead peer must not hang the GPU forever
         if (error_flag) atomicExch(error_flag, 1 + p);
         break;

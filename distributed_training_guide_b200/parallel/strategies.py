@@ -244,6 +244,11 @@ class FullyShardedDataParallel(Strategy):
         from .fsdp import FSDPEngine
 
         env = self.env
+        if getattr(args, "cpu_offload", False):
+            # the CPU optimizer is the critical path with offload: give every rank its share of the cores
+            # (reference 05-training-llama-405b/train_llm.py:69-72; torchrun defaults OMP_NUM_THREADS to 1)
+            ngpu = max(1, torch.cuda.device_count() if torch.cuda.is_available() else 1)
+            torch.set_num_threads(max(torch.get_num_threads(), (os.cpu_count() or 1) // ngpu))
         with self.data_guard():
             model = build_model(config, dtype=self.dtype(), device="meta", init=False)
         if env.device.type == "cuda":

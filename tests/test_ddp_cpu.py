@@ -7,13 +7,9 @@ from dist_utils import run_distributed
 
 def _train(rank, world, parallelism, steps, zero1):
     from distributed_training_guide_b200.engine import TrainEngine
-    from distributed_training_guide_b200.parallel import strategies as S
-
     torch.manual_seed(0)
     eng = TrainEngine.create("debug-llama", parallelism=parallelism, batch_size=2, seq_length=32, device="cpu",
                              lr=1e-3)
-    if parallelism == "ddp" and not zero1:
-        pass
     losses = []
     for i in range(steps):
         b = eng.synthetic_batch(seed=i, pinned=False)

@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU session: numerics of the simple kernels + tcgen05 GEMM (both variants), GEMM throughput
 # vs cuBLAS, and the two bench arms at N=1.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 export DTG_TEST_TIMEOUT=300
 tools/run_gpu_checks.sh tests/test_gpu_elementwise.py

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "=== all 1-GPU tests"
 timeout --signal=KILL 900 python -m pytest tests/ -m gpu -q --no-header -p no:cacheprovider > gpurun_out/pytest_gpu_all.log 2>&1; echo "exit=$?" >> gpurun_out/pytest_gpu_all.log; tail -n 5 gpurun_out/pytest_gpu_all.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # 2-GPU session: chapter scripts on GPUs, multi-GPU tests, N=2 benches after the 128-bit fix
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "=== chapter + multi-GPU tests"
 timeout --signal=KILL 1200 python -m pytest tests/test_gpu_chapters.py tests/test_gpu_tp.py tests/test_gpu_comm.py -m gpu -q --no-header -p no:cacheprovider -x > gpurun_out/pytest_s12.log 2>&1; echo "exit=$?" >> gpurun_out/pytest_s12.log; tail -n 25 gpurun_out/pytest_s12.log | cut -c1-300

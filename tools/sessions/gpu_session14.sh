@@ -1,6 +1,6 @@
 #!/bin/bash
 # 4-GPU session: first run at N=4 (DDP bench + trace, FSDP, 2-D dp2 x tp2 chapter run and 7B bench)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "=== 2-D chapter on 4 GPUs + comm tests"
 timeout --signal=KILL 900 python -m pytest tests/test_gpu_chapters.py::test_2d_dp2_tp2_on_four_gpus tests/test_gpu_comm.py -m gpu -q --no-header -p no:cacheprovider > gpurun_out/pytest_s14.log 2>&1; echo "exit=$?" >> gpurun_out/pytest_s14.log; tail -n 12 gpurun_out/pytest_s14.log | cut -c1-300

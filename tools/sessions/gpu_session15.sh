@@ -1,6 +1,6 @@
 #!/bin/bash
 # 4-GPU session: 2-D (dp2 x tp2) after the norm-scratch fix
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout --signal=KILL 600 python -m pytest tests/test_gpu_chapters.py::test_2d_dp2_tp2_on_four_gpus -m gpu -q --no-header -p no:cacheprovider > gpurun_out/pytest_s15.log 2>&1; echo "exit=$?" >> gpurun_out/pytest_s15.log; tail -n 12 gpurun_out/pytest_s15.log | cut -c1-300
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29511"

@@ -1,6 +1,6 @@
 #!/bin/bash
 # 1-GPU session: sustained (power-capped) GEMM vs cuBLAS, large-model shapes, ncu of the fixed GEMM, bench sanity
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "=== sustained gemm"
 timeout --signal=KILL 400 python tools/gemm_sustained.py --seconds 2.0 > gpurun_out/gemm_sustained.log 2>&1; tail -n 8 gpurun_out/gemm_sustained.log | cut -c1-400

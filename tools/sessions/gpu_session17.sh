@@ -1,6 +1,6 @@
 #!/bin/bash
 # 1-GPU session: L2-aware tile order: numerics, sustained GEMM with and without grouping, shapes test, bench
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "=== gemm tests"
 timeout --signal=KILL 600 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_shapes.py -m gpu -q --no-header -p no:cacheprovider > gpurun_out/pytest_s17.log 2>&1; echo "exit=$?" >> gpurun_out/pytest_s17.log; tail -n 8 gpurun_out/pytest_s17.log | cut -c1-300

@@ -1,6 +1,6 @@
 #!/bin/bash
 # 8-GPU session: headline DDP+ZeRO-1 bench, FSDP, 2-D (dp4 x tp2), each with the communication trace
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511"
 run() { name=$1; shift

@@ -1,6 +1,6 @@
 #!/bin/bash
 # 2-GPU session: TP with optimizer-in-backward, cpu-offload chapter test, N=2 benches with fresh batches
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "=== chapter + TP tests"
 timeout --signal=KILL 1200 python -m pytest tests/test_gpu_chapters.py tests/test_gpu_tp.py -m gpu -q --no-header -p no:cacheprovider > gpurun_out/pytest_s19.log 2>&1; echo "exit=$?" >> gpurun_out/pytest_s19.log; tail -n 12 gpurun_out/pytest_s19.log | cut -c1-300

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Session 2 (1 GPU): re-check elementwise + gemm autograd, attention numerics/perf, ncu of both GEMM variants.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 export DTG_TEST_TIMEOUT=300
 tools/run_gpu_checks.sh tests/test_gpu_elementwise.py

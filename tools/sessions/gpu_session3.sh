@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 export DTG_TEST_TIMEOUT=300
 timeout --signal=KILL 200 python -m pytest tests/test_gpu_elementwise.py -m gpu -q --no-header -p no:cacheprovider -k rope > gpurun_out/rope.log 2>&1; tail -n 3 gpurun_out/rope.log

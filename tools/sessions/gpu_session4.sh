@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "=== attention numerics (2 threads/row rewrite)"
 timeout --signal=KILL 300 python -m pytest tests/test_gpu_attention.py -m gpu -q --no-header -p no:cacheprovider > gpurun_out/attention.log 2>&1; echo "exit=$?" >> gpurun_out/attention.log; tail -n 12 gpurun_out/attention.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # 2-GPU session: NVLink collectives vs NCCL, DDP+ZeRO-1 parity, bench at N=2 (own + reference), N=1 re-check
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/topo.txt 2>&1
 echo "=== comm tests (2 GPUs)"

@@ -1,6 +1,6 @@
 #!/bin/bash
 # 2-GPU session: tensor-parallel fused GEMM modes + TP/FSDP engines vs single GPU, benches for fsdp / tp at N=2
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "=== TP / FSDP GPU tests"
 timeout --signal=KILL 900 python -m pytest tests/test_gpu_tp.py -m gpu -q --no-header -p no:cacheprovider -s > gpurun_out/tp_tests.log 2>&1; echo "exit=$?" >> gpurun_out/tp_tests.log; tail -n 30 gpurun_out/tp_tests.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # 2 GPUs: attention pipeline trace (GPU 0), host-side profile of a TP step, phase timing of TP / FSDP
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "=== attention bwd in-kernel trace"
 timeout --signal=KILL 200 python tools/trace_attn.py > gpurun_out/attn_trace.log 2>&1; tail -n 34 gpurun_out/attn_trace.log

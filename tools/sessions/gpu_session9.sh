@@ -1,6 +1,6 @@
 #!/bin/bash
 # 8-GPU session: headline bench (DDP+ZeRO-1) at N=8, FSDP at N=8, collectives bandwidth at N=8
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/topo8.txt 2>&1
 echo "=== bench own N=8 (ddp + zero1)"

@@ -32,6 +32,7 @@ import torch
 import torch.distributed as dist
 from torch.autograd import Variable
 
+from ..utils.timers import nvtx_range
 from .flat import FlatGroup
 from .optim import FlatAdamW
 
@@ -177,6 +178,10 @@ class DataParallelEngine:
                 "tail_ms": round(sum(tails) / len(tails), 3) if tails else None}
 
     def _run_bucket(self, g, gbuf):
+        with nvtx_range(f"bucket:{g.name}"):
+            self._run_bucket_impl(g, gbuf)
+
+    def _run_bucket_impl(self, g, gbuf):
         opt = self.optimizer
         if self.zero1:
             st = opt.state[g.param]

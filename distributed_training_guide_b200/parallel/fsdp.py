@@ -35,6 +35,7 @@ from torch.autograd import Variable
 
 from ..models.llama import FusedWeight, LlamaDecoderLayer, init_parameter_
 from ..ops import reference as ref
+from ..utils.timers import nvtx_range
 from .ddp import boundary
 from .flat import ALIGN, FlatGroup, _round_up
 from .optim import FlatAdamW
@@ -230,8 +231,9 @@ class FSDPEngine:
                 if ev is not None:
                     self.comm_stream.wait_event(ev)  # the slot's previous layer has finished computing
             t0 = self._trace_begin()
-            self.symm.allgather_(self._symm_of[sh.param.data_ptr()], g.param, 0, sh.padded_numel,
-                                 copy_engine=self.ag_copy_engine)
+            with nvtx_range(f"unshard:{g.name}"):
+                self.symm.allgather_(self._symm_of[sh.param.data_ptr()], g.param, 0, sh.padded_numel,
+                                     copy_engine=self.ag_copy_engine)
             self._trace_end("unshard", t0)
             ev = torch.cuda.Event()
             ev.record(self.comm_stream)
@@ -368,8 +370,9 @@ class FSDPEngine:
                 st["cpu_grad"].copy_(st["gpu_grad"], non_blocking=True)
             else:
                 t0 = self._trace_begin()
-                self.symm.rs_adamw_(gbuf, None, sh.param, st["exp_avg"], st["exp_avg_sq"], False, 0, g.padded_numel,
-                                    opt.hyper(), st["step"], opt.grad_scale / self.world)
+                with nvtx_range(f"reduce_adamw:{g.name}"):
+                    self.symm.rs_adamw_(gbuf, None, sh.param, st["exp_avg"], st["exp_avg_sq"], False, 0,
+                                        g.padded_numel, opt.hyper(), st["step"], opt.grad_scale / self.world)
                 self._trace_end("reduce_adamw", t0)
             done = torch.cuda.Event()
             done.record(self.comm_stream)

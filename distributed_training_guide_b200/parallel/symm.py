@@ -142,7 +142,22 @@ class SymmGroup:
         """Raise if a device-side barrier timed out (a peer died or diverged)."""
         v = int(self.err.item())
         if v:
-            raise RuntimeError(f"NVLink barrier timed out waiting for rank {v - 1} (group rank {self.rank})")
+            raise RuntimeError(f"NVLink barrier timed out waiting for rank {v - 1} (group rank {self.rank}); "
+                               + self.describe_pads())
+
+    def describe_pads(self) -> str:
+        """Signal-pad state for a post-mortem: per peer, the range of epochs this rank has received over its
+        channels, next to the epoch this rank's host has issued.  A peer stuck at a lower epoch never launched
+        (or never finished) the matching collective."""
+        try:
+            ch = int(self.C.SYMM_MAX_CHANNELS)
+            mr = int(self.C.SYMM_PAD_BYTES) // 4 // ch           # uint32 [channels][max ranks]
+            words = self.pads.local[: ch * mr * 4].view(torch.int32)
+            tab = words.view(ch, mr)[: self.comm_blocks, : self.world].cpu()
+            seen = ", ".join(f"rank {p}: {int(tab[:, p].min())}..{int(tab[:, p].max())}" for p in range(self.world))
+            return f"epochs received per peer (min..max over {self.comm_blocks} channels): {seen}; issued locally: {self.epoch}"
+        except Exception as e:  # pragma: no cover - best effort diagnostics
+            return f"(pad state unavailable: {e})"
 
     def close(self):
         for p in self._peer_handles:

@@ -89,7 +89,7 @@ def train(args, strategy):
 
     tracker = strategy.build_tracker(args, exp_dir if is_experiment else None, resumed, config)
 
-    timers = {k: LocalTimer(device) for k in ["data", "forward", "backward", "update"]}
+    timers = {k: LocalTimer(device, name=k) for k in ["data", "forward", "backward", "update"]}
     accum = max(1, getattr(args, "grad_accum_steps", 1))
     running_loss = torch.zeros((), dtype=torch.float32, device=device)
     if resumed:

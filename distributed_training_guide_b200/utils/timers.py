@@ -9,13 +9,32 @@ resolved lazily when ``avg_elapsed_ms()`` is read (once per ``--log-freq`` steps
 """
 from __future__ import annotations
 
+import os
 import time
+from contextlib import contextmanager
 
 import torch
 
+NVTX = bool(os.environ.get("DTG_NVTX"))
+
+
+@contextmanager
+def nvtx_range(name: str):
+    """``DTG_NVTX=1``: NVTX range around a phase / fused path, so a profiler timeline (nsys, ncu --nvtx) shows
+    data / forward / backward / update and every bucket or unshard launch by name.  Free when off."""
+    on = NVTX and torch.cuda.is_available()
+    if on:
+        torch.cuda.nvtx.range_push(name)
+    try:
+        yield
+    finally:
+        if on:
+            torch.cuda.nvtx.range_pop()
+
 
 class LocalTimer:
-    def __init__(self, device: torch.device, sync: bool = False):
+    def __init__(self, device: torch.device, sync: bool = False, name: str = ""):
+        self.name = name
         self.device = torch.device(device)
         self.is_cuda = self.device.type == "cuda"
         self.sync = sync  # reference-style host-synchronous timing (used by diagnostics)
@@ -27,6 +46,8 @@ class LocalTimer:
             torch.cuda.synchronize(self.device)
 
     def __enter__(self):
+        if NVTX and self.is_cuda and self.name:
+            torch.cuda.nvtx.range_push(self.name)
         if self.is_cuda and not self.sync:
             self._start = torch.cuda.Event(enable_timing=True)
             self._start.record()
@@ -36,6 +57,8 @@ class LocalTimer:
         return self
 
     def __exit__(self, exc_type, exc, tb):
+        if NVTX and self.is_cuda and self.name:
+            torch.cuda.nvtx.range_pop()
         if tb is None:
             if self.is_cuda and not self.sync:
                 end = torch.cuda.Event(enable_timing=True)

@@ -18,7 +18,6 @@ What is *different* from the HF module code is the execution p
 """
 from __future__ import annotations
 
-import math
 from types import SimpleNamespace
 from typing import Optional
 

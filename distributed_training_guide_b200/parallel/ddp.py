@@ -26,7 +26,7 @@ from __future__ import annotations
 
 import contextlib
 import os
-from typing import List, Optional
+from typing import List
 
 import torch
 import torch.distributed as dist

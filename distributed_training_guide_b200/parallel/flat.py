@@ -15,7 +15,6 @@ second contiguous buffer for its gradients:
 """
 from __future__ import annotations
 
-import math
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch

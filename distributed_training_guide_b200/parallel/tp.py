@@ -29,9 +29,7 @@ gather / after a push).  On CPU (gloo tests) every op falls back to ``torch.dist
 """
 from __future__ import annotations
 
-import math
 from types import SimpleNamespace
-from typing import Optional
 
 import torch
 import torch.distributed as dist

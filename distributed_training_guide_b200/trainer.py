@@ -15,9 +15,6 @@ logged.
 from __future__ import annotations
 
 import logging
-import math
-import time
-from pathlib import Path
 
 import torch
 import torch.distributed as dist
@@ -26,7 +23,7 @@ from .models import get_config
 from .utils import ckpt as ckpt_utils
 from .utils import data as data_utils
 from .utils.logging import setup_logging
-from .utils.lr import cosine_schedule, scale_lr
+from .utils.lr import scale_lr
 from .utils.mem import get_mem_stats, reset_peak
 from .utils.timers import LocalTimer
 

@@ -34,6 +34,28 @@ __all__ = [
 # --------------------------------------------------------------------------------------
 # helpers
 # --------------------------------------------------------------------------------------
+# EXPERIMENTAL (DTG_WGRAD_STREAM=1, off by default): issue the weight-gradient GEMM of a linear layer on a side
+# stream so that it runs next to the data-gradient GEMM of the same layer; both are persistent kernels, so the
+# CTAs of one fill the SMs the other leaves idle in its last partial wave.  Engines call ``join_wgrad_stream()``
+# before they publish a bucket's gradients.
+_WGRAD_SIDE = {"enabled": bool(__import__("os").environ.get("DTG_WGRAD_STREAM")), "stream": None, "dirty": False}
+
+
+def _wgrad_stream(device):
+    st = _WGRAD_SIDE
+    if st["stream"] is None:
+        st["stream"] = torch.cuda.Stream(device=device)
+    return st["stream"]
+
+
+def join_wgrad_stream():
+    """Make the current stream wait for weight gradients issued on the side stream (no-op when the feature is off)."""
+    st = _WGRAD_SIDE
+    if st["dirty"]:
+        torch.cuda.current_stream().wait_stream(st["stream"])
+        st["dirty"] = False
+
+
 def _emit_weight_grad(param, compute_into, shape_like):
     """Route a weight gradient.
 
@@ -104,11 +126,22 @@ class _Linear(torch.autograd.Function):
             dx = gemm(dy2, w).view(ctx.x_shape)  # [T,N] @ [N,K]
         dw = None
         if ctx.needs_input_grad[1] or getattr(ctx.w_param, "_dtg_grad", None) is not None:
-            dw = _emit_weight_grad(
-                ctx.w_param,
-                lambda out, acc: gemm(dy2, x2, out=out, trans_a=True, accumulate=acc),  # dy^T @ x
-                w,
-            )
+            side = _WGRAD_SIDE["enabled"] and dy2.is_cuda and getattr(ctx.w_param, "_dtg_grad", None) is not None
+            if side:
+                cur, ss = torch.cuda.current_stream(), _wgrad_stream(dy2.device)
+                ss.wait_stream(cur)               # dy2 / x2 were produced on the compute stream
+                dy2.record_stream(ss)             # keep the caching allocator from recycling them too early
+                x2.record_stream(ss)
+                with torch.cuda.stream(ss):
+                    dw = _emit_weight_grad(ctx.w_param,
+                                           lambda out, acc: gemm(dy2, x2, out=out, trans_a=True, accumulate=acc), w)
+                _WGRAD_SIDE["dirty"] = True
+            else:
+                dw = _emit_weight_grad(
+                    ctx.w_param,
+                    lambda out, acc: gemm(dy2, x2, out=out, trans_a=True, accumulate=acc),  # dy^T @ x
+                    w,
+                )
         return dx, dw, None
 
 

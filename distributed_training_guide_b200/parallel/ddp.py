@@ -32,6 +32,7 @@ import torch
 import torch.distributed as dist
 from torch.autograd import Variable
 
+from ..ops import join_wgrad_stream
 from ..utils.timers import nvtx_range
 from .flat import FlatGroup
 from .optim import FlatAdamW
@@ -140,6 +141,7 @@ class DataParallelEngine:
         if not self.use_kernels:
             self._launch_fallback(g)
             return
+        join_wgrad_stream()
         ev = torch.cuda.Event()
         ev.record()  # on the compute stream: this bucket's wgrad kernels are all enqueued before it
         gbuf = self.registry[g.grad.data_ptr()]
@@ -242,6 +244,7 @@ class LocalOverlapEngine(DataParallelEngine):
         if not self.use_kernels:
             self.optimizer.step_group(g)
             return
+        join_wgrad_stream()
         ev = torch.cuda.Event()
         ev.record()
         with torch.cuda.stream(self.comm_stream):

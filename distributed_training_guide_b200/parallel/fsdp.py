@@ -35,6 +35,7 @@ from torch.autograd import Variable
 
 from ..models.llama import FusedWeight, LlamaDecoderLayer, init_parameter_
 from ..ops import reference as ref
+from ..ops import join_wgrad_stream
 from ..utils.timers import nvtx_range
 from .ddp import boundary
 from .flat import ALIGN, FlatGroup, _round_up
@@ -358,6 +359,7 @@ class FSDPEngine:
             ref.adamw_step(sh.param, gshard.to(sh.param.dtype), st["exp_avg"], st["exp_avg_sq"], lr, b1, b2, eps, wd,
                            st["step"], opt.grad_scale)
             return
+        join_wgrad_stream()
         ev = torch.cuda.Event()
         ev.record()
         gbuf = self._symm_of[g.grad.data_ptr() if g.name in ("embed", "head") else

@@ -112,6 +112,27 @@ void rs_adamw(const std::vector<uint64_t>& grads, const std::vector<uint64_t>& p
                 (uint32_t)epoch, err_ptr(err), (int)blocks, stream());
 }
 
+// ---- NVLS (multicast) variants ----------------------------------------------------------------------------------
+void nvls_allreduce_scale(uint64_t mc, const std::vector<uint64_t>& pads, int64_t elem_off, int64_t n, double scale,
+                          int64_t rank, int64_t epoch, const c10::optional<Tensor>& err, int64_t blocks) {
+  comm_nvls_allreduce_scale((void*)mc, pads_of(pads), (size_t)elem_off, (size_t)n, (float)scale, (int)rank,
+                            (int)pads.size(), (uint32_t)epoch, err_ptr(err), (int)blocks, stream());
+}
+
+void nvls_rs_adamw(uint64_t grads_mc, uint64_t params_mc, uint64_t params_local, Tensor& m, Tensor& v,
+                   const std::vector<uint64_t>& pads, int64_t elem_off, int64_t n, double lr, double b1, double b2,
+                   double eps, double wd, int64_t step, double grad_scale, int64_t rank, int64_t epoch,
+                   const c10::optional<Tensor>& err, int64_t blocks) {
+  const bool fp32 = m.scalar_type() == at::kFloat;
+  TORCH_CHECK(m.scalar_type() == v.scalar_type() && (fp32 || m.scalar_type() == at::kBFloat16), "bad state dtype");
+  const int nr = (int)pads.size();
+  TORCH_CHECK(m.numel() * nr == n && v.numel() * nr == n, "optimizer shard must hold n / nranks elements");
+  AdamWHyper hp = make_adamw_hyper((float)lr, (float)b1, (float)b2, (float)eps, (float)wd, (int)step, (float)grad_scale);
+  comm_nvls_rs_adamw((const void*)grads_mc, (void*)params_mc, (const void*)params_local, m.data_ptr(), v.data_ptr(), fp32,
+                     pads_of(pads), (size_t)elem_off, (size_t)n, hp, (int)rank, nr, (uint32_t)epoch, err_ptr(err),
+                     (int)blocks, stream());
+}
+
 void allgather(const std::vector<uint64_t>& shards, Tensor& full, const std::vector<uint64_t>& pads, int64_t shard_off,
                int64_t per, int64_t rank, int64_t epoch, const c10::optional<Tensor>& err, bool barrier,
                int64_t blocks) {
@@ -151,6 +172,8 @@ void bind_comm(pybind11::module_& m) {
   m.def("comm_allreduce_scale", &allreduce_scale);
   m.def("comm_rs_adamw", &rs_adamw);
   m.def("comm_allgather", &allgather);
+  m.def("comm_nvls_allreduce_scale", &nvls_allreduce_scale);
+  m.def("comm_nvls_rs_adamw", &nvls_rs_adamw);
   m.def("comm_reduce_scatter", &reduce_scatter);
   m.def("comm_barrier", &barrier);
 }

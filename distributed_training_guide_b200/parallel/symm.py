@@ -12,6 +12,7 @@ single-GPU chapter shares the fused optimizer path.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
@@ -28,12 +29,15 @@ def allocated_bytes() -> int:
 
 
 class SymmBuffer:
-    """One symmetric allocation: ``local`` (this rank's memory as a tensor) + every rank's base pointer."""
+    """One symmetric allocation: ``local`` (this rank's memory as a tensor) + every rank's base pointer
+    (+ the NVSwitch multicast address of the allocation when it was bound to one, else 0)."""
 
-    def __init__(self, local: torch.Tensor, ptrs: List[int], raw: torch.Tensor):
+    def __init__(self, local: torch.Tensor, ptrs: List[int], raw: torch.Tensor, mc_ptr: int = 0, handle=None):
         self.local = local
         self.ptrs = ptrs
-        self._raw = raw  # keeps the cudaMalloc alive
+        self._raw = raw  # keeps the allocation alive
+        self.mc_ptr = int(mc_ptr or 0)
+        self._handle = handle
 
     def elem_offset_of(self, view: torch.Tensor) -> int:
         off = view.data_ptr() - self.local.data_ptr()
@@ -59,19 +63,39 @@ class SymmGroup:
             # it needs the whole chip to reach memory bandwidth.  Several ranks: enough CTAs to keep
             # ~1 MB of 16-byte NVLink loads in flight (~2 us latency x ~800 GB/s) without starving the
             # tensor-core kernels it overlaps with.
-            import os
-
             comm_blocks = int(os.environ.get("DTG_COMM_BLOCKS", 256 if self.world == 1 else 96))
         self.comm_blocks = min(comm_blocks, int(self.C.SYMM_MAX_CHANNELS))
         self._peer_handles = []
         self.epoch = 0
+        # EXPERIMENTAL (DTG_NVLS=1): allocate through torch.distributed._symmetric_memory so every buffer is also
+        # bound to an NVSwitch multicast address; the bucket kernels then reduce in the switch (comm_nvls.cu).
+        self.nvls = bool(os.environ.get("DTG_NVLS")) and self.world > 1
         self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.pads = self.alloc_bytes(int(self.C.SYMM_PAD_BYTES))
         self.pad_ptrs = self.pads.ptrs
         _LIVE_GROUPS.append(self)
 
     # -- allocation -----------------------------------------------------------------------------
+    def _alloc_bytes_multicast(self, nbytes: int) -> SymmBuffer:
+        import torch.distributed._symmetric_memory as symm_mem
+
+        pg = self.pg if self.pg is not None else dist.group.WORLD
+        try:
+            symm_mem.enable_symm_mem_for_group(pg.group_name)
+        except Exception:
+            pass  # newer torch enables groups on demand
+        raw = symm_mem.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        hdl = symm_mem.rendezvous(raw, pg)
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        if mc == 0:
+            raise RuntimeError("DTG_NVLS=1 but this system exposes no NVSwitch multicast (NVLS) address")
+        raw.zero_()
+        return SymmBuffer(raw, ptrs, raw, mc_ptr=mc, handle=hdl)
+
     def alloc_bytes(self, nbytes: int) -> SymmBuffer:
+        if self.nvls:
+            return self._alloc_bytes_multicast(nbytes)
         raw, handle = self.C.symm_alloc(int(nbytes), self.device.index or 0)
         if self.world == 1:
             ptrs = [raw.data_ptr()]
@@ -113,12 +137,21 @@ class SymmGroup:
         return e
 
     def allreduce_scale_(self, buf: SymmBuffer, elem_off: int, n: int, scale: float, blocks: Optional[int] = None):
+        if self.nvls and buf.mc_ptr:
+            self.C.comm_nvls_allreduce_scale(buf.mc_ptr, self.pad_ptrs, elem_off, n, scale, self.rank, self._epochs(2),
+                                             self.err, blocks or self.comm_blocks)
+            return
         self.C.comm_allreduce_scale(buf.ptrs, self.pad_ptrs, elem_off, n, scale, self.rank, self._epochs(2), self.err,
                                     blocks or self.comm_blocks)
 
     def rs_adamw_(self, grads: SymmBuffer, params: Optional[SymmBuffer], param_local, m, v, push_params: bool,
                   elem_off: int, n: int, hyper, step: int, grad_scale: float, blocks: Optional[int] = None):
         lr, b1, b2, eps, wd = hyper
+        if self.nvls and push_params and grads.mc_ptr and params is not None and params.mc_ptr:
+            self.C.comm_nvls_rs_adamw(grads.mc_ptr, params.mc_ptr, params.ptrs[self.rank], m, v, self.pad_ptrs, elem_off,
+                                      n, lr, b1, b2, eps, wd, step, grad_scale, self.rank, self._epochs(2), self.err,
+                                      blocks or self.comm_blocks)
+            return
         self.C.comm_rs_adamw(grads.ptrs, params.ptrs if params is not None else [], param_local, m, v, push_params,
                              self.pad_ptrs, elem_off, n, lr, b1, b2, eps, wd, step, grad_scale, self.rank,
                              self._epochs(2), self.err, blocks or self.comm_blocks)

@@ -152,3 +152,76 @@ def test_ddp_zero1_gpu_matches_single_gpu():
         assert np.array_equal(sd0[k], sd1[k]), f"replicas diverged: {k}"
     for i in range(steps):
         assert abs(0.5 * (l0[i] + l1[i]) - ref[i]) < 5e-2, (i, l0[i], l1[i], ref[i])
+
+
+def _nvls_checks(rank, world):
+    """The same two checks as above through the NVSwitch-multicast kernels (DTG_NVLS=1, comm_nvls.cu)."""
+    import os
+
+    os.environ["DTG_NVLS"] = "1"
+    import torch.distributed as dist
+
+    from distributed_training_guide_b200.parallel import bootstrap
+    from distributed_training_guide_b200.parallel.symm import SymmGroup
+
+    env = bootstrap.init_distributed("cuda")
+    dev = env.device
+    try:
+        sg = SymmGroup(dev)
+    except Exception as e:  # no multicast support on this box / torch build
+        return {"skipped": f"{type(e).__name__}: {e}"}
+    assert sg.nvls and sg.pads.mc_ptr
+    out = {}
+    n = 8 * world * 12345
+    torch.manual_seed(100 + rank)
+    buf = sg.alloc(n, torch.bfloat16)
+    x = torch.randn(n, device=dev).to(torch.bfloat16)
+    buf.local.copy_(x)
+    want = x.float().clone()
+    dist.all_reduce(want)
+    want = want / world
+    torch.cuda.synchronize()
+    dist.barrier()
+    sg.allreduce_scale_(buf, 0, n, 1.0 / world)
+    torch.cuda.synchronize()
+    out["allreduce_err"] = (buf.local.float() - want).abs().max().item()
+    g = sg.alloc(n, torch.bfloat16)
+    p = sg.alloc(n, torch.bfloat16)
+    torch.manual_seed(7)
+    p0 = torch.randn(n, device=dev).to(torch.bfloat16)
+    p.local.copy_(p0)
+    torch.manual_seed(200 + rank)
+    gl = (0.01 * torch.randn(n, device=dev)).to(torch.bfloat16)
+    g.local.copy_(gl)
+    gsum = gl.float().clone()
+    dist.all_reduce(gsum)
+    per = n // world
+    m = torch.zeros(per, device=dev, dtype=torch.bfloat16)
+    v = torch.zeros(per, device=dev, dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sg.rs_adamw_(g, p, None, m, v, True, 0, n, (1e-2, 0.9, 0.999, 1e-8, 1e-2), 1, 1.0 / world)
+    torch.cuda.synchronize()
+    dist.barrier()
+    pr = torch.nn.Parameter(p0.float().clone())
+    opt = torch.optim.AdamW([pr], lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    pr.grad = gsum / world
+    opt.step()
+    out["zero1_err"] = (p.local.float() - pr.data).abs().max().item()
+    chk = p.local.float().clone()
+    dist.broadcast(chk, src=0)
+    out["zero1_replica_diff"] = (chk - p.local.float()).abs().max().item()
+    sg.check()
+    return out
+
+
+def test_nvls_collectives():
+    world = _world()
+    res = run_distributed(_nvls_checks, world=world, timeout=300)
+    if "skipped" in res[0]:
+        pytest.skip(res[0]["skipped"])
+    print(res[0])
+    for r in res:
+        assert r["allreduce_err"] < 0.05, r
+        assert r["zero1_err"] < 0.05, r
+        assert r["zero1_replica_diff"] == 0.0, r

@@ -10,7 +10,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 SO = ROOT / "distributed_training_guide_b200" / "_C.so"
 COLS = ["UTCHMMA", "UTCBAR", "UTCATOMSWS", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "HMMA", "MUFU.EX2",
-        "LDG.E.128", "STG.E.128", "LDG.E ", "STG.E ", "MEMBAR", "RED", "ATOM"]
+        "LDGMC", "LDG.E.128", "STG.E.128", "LDG.E ", "STG.E ", "MEMBAR", "RED", "ATOM"]
 
 
 def _strip_params(name):
@@ -48,7 +48,7 @@ def main():
     out = ["# SASS evidence per kernel (`cuobjdump -sass distributed_training_guide_b200/_C.so`, sm_100a)", "",
            "Regenerate with `python tools/sass_summary.py`.  `UTCHMMA` = tcgen05.mma, `LDTM`/`STTM` = tcgen05.ld/st, `UTMALDG` = TMA",
            "load, `UBLKCP` = cp.async.bulk, `UTCBAR` = tcgen05.commit, `UTCATOMSWS` = TMEM alloc, `SYNCS` = mbarrier ops; `HMMA` would",
-           "be the legacy mma.sync path (none expected).  `LDG.E.128`/`STG.E.128` vs the 32-bit `LDG.E`/`STG.E` columns show that the",
+           "be the legacy mma.sync path (none expected).  `LDGMC` = multimem.ld_reduce (in-switch NVLS reduction).  `LDG.E.128`/`STG.E.128` vs the 32-bit `LDG.E`/`STG.E` columns show that the",
            "streaming kernels move 16 bytes per instruction.", "",
            "| kernel | " + " | ".join(c.strip() + ("(32b)" if c.endswith(" ") else "") for c in COLS) + " |",
            "|---|" + "---|" * len(COLS)]

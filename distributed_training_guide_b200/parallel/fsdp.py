@@ -26,6 +26,7 @@ On CPU (gloo tests) the same schedule runs with ``torch.distributed`` collective
 """
 from __future__ import annotations
 
+import contextlib
 import os
 from typing import Dict, List, Optional
 
@@ -337,13 +338,28 @@ class FSDPEngine:
         if self.use_kernels:
             self._done.record(self.comm_stream)
 
+    @contextlib.contextmanager
+    def no_sync(self):
+        """Gradient accumulation (``--grad-accum-steps``): inside this context a micro-batch's gradients are still
+        reduce-scattered (the gradient slots rotate between layers, nothing full-size survives a micro-batch) but
+        only ACCUMULATED into an fp32 shard-sized buffer; the optimizer runs on the boundary micro-batch."""
+        old, self.sync_enabled = self.sync_enabled, False
+        try:
+            yield
+        finally:
+            self.sync_enabled = old
+
     def _reduce(self, g: FlatGroup):
-        """reduce-scatter(mean) of ``g``'s gradient slot fused with AdamW on this rank's shard."""
+        """reduce-scatter(mean) of ``g``'s gradient slot fused with AdamW on this rank's shard.  While gradients are
+        being accumulated over micro-batches the reduce-scatter lands in an fp32 shard accumulator instead and AdamW
+        runs once, on the boundary."""
         sh = self.shard_of[g.name]
         opt = self.optimizer
         st = opt.state[sh.param]
         if self.pre_reduce is not None:
             self.pre_reduce(g)
+        boundary = self.sync_enabled
+        accumulating = (not boundary) or st.get("acc_pending", False)
         if not self.use_kernels:
             if self.world > 1:
                 buf = g.grad.float()
@@ -351,6 +367,17 @@ class FSDPEngine:
                 gshard = (buf / self.world)[self.rank * sh.padded_numel:(self.rank + 1) * sh.padded_numel]
             else:
                 gshard = g.grad.float()
+            g.zero_grad_counters()  # the next write into this gradient buffer opens a new window
+            if accumulating:
+                if "acc" not in st:
+                    st["acc"] = torch.zeros(sh.padded_numel, dtype=torch.float32, device=gshard.device)
+                st["acc"].add_(gshard)
+                st["acc_pending"] = True
+                if not boundary:
+                    return
+                gshard = st["acc"].clone()
+                st["acc"].zero_()
+                st["acc_pending"] = False
             st["step"] += 1
             if self.cpu_offload:  # the update itself happens in optimizer.step() on the host copies
                 st["cpu_grad"].copy_((gshard * opt.grad_scale).to(st["cpu_grad"].dtype))
@@ -364,17 +391,39 @@ class FSDPEngine:
         ev.record()
         gbuf = self._symm_of[g.grad.data_ptr() if g.name in ("embed", "head") else
                              self.grad_slots[self.gslot_of[g.name]].data_ptr()]
+        g.zero_grad_counters()
         with torch.cuda.stream(self.comm_stream):
             self.comm_stream.wait_event(ev)
-            st["step"] += 1
-            if self.cpu_offload:
-                self.symm.reduce_scatter_(gbuf, st["gpu_grad"], 0, g.padded_numel, opt.grad_scale / self.world)
+            scale = opt.grad_scale / self.world
+            if accumulating:
+                if "gpu_grad" not in st:
+                    st["gpu_grad"] = torch.zeros_like(sh.param)
+                if "acc" not in st:
+                    st["acc"] = torch.zeros(sh.padded_numel, dtype=torch.float32, device=sh.param.device)
+                self.symm.reduce_scatter_(gbuf, st["gpu_grad"], 0, g.padded_numel, scale)
+                st["acc"].add_(st["gpu_grad"])
+                st["acc_pending"] = True
+                if boundary:
+                    st["step"] += 1
+                    st["gpu_grad"].copy_(st["acc"])
+                    st["acc"].zero_()
+                    st["acc_pending"] = False
+                    if self.cpu_offload:
+                        st["cpu_grad"].copy_(st["gpu_grad"], non_blocking=True)
+                    else:
+                        lr, b1, b2, eps, wd = opt.hyper()
+                        self.symm.C.adamw_flat(sh.param, st["gpu_grad"], st["exp_avg"], st["exp_avg_sq"], lr, b1, b2,
+                                               eps, wd, st["step"], 1.0)
+            elif self.cpu_offload:
+                st["step"] += 1
+                self.symm.reduce_scatter_(gbuf, st["gpu_grad"], 0, g.padded_numel, scale)
                 st["cpu_grad"].copy_(st["gpu_grad"], non_blocking=True)
             else:
+                st["step"] += 1
                 t0 = self._trace_begin()
                 with nvtx_range(f"reduce_adamw:{g.name}"):
                     self.symm.rs_adamw_(gbuf, None, sh.param, st["exp_avg"], st["exp_avg_sq"], False, 0,
-                                        g.padded_numel, opt.hyper(), st["step"], opt.grad_scale / self.world)
+                                        g.padded_numel, opt.hyper(), st["step"], scale)
                 self._trace_end("reduce_adamw", t0)
             done = torch.cuda.Event()
             done.record(self.comm_stream)

@@ -267,6 +267,11 @@ class FullyShardedDataParallel(Strategy):
     def num_parameters(self, model):
         return model.config.num_parameters()
 
+    def grad_sync(self, model, enabled=True):
+        if enabled or self.engine is None:
+            return contextlib.nullcontext()
+        return self.engine.no_sync()
+
     def build_optimizer(self, args, model, lr):
         return self.engine.build_optimizer(lr)
 

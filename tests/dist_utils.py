@@ -61,3 +61,27 @@ def run_distributed(fn, world=2, args=(), timeout=300):
             if p.is_alive():
                 p.kill()
     return [results[r] for r in range(world)]
+
+
+def update_rel_err(init, got, ref):
+    """Relative L2 error of the *update* (final - initial weights) of ``got`` against ``ref``.  Max-abs differences of
+    the weights themselves are dominated by sign flips of near-zero gradients under Adam (each costs 2*lr) and say
+    little; a wrong number of optimizer steps or a wrong accumulation moves this metric to ~1, a correct engine sits
+    at a few percent (bf16 rounding)."""
+    import numpy as np
+
+    keys = sorted(ref)
+    f = lambda d: np.concatenate([np.asarray(d[k], dtype=np.float64).ravel() for k in keys])  # noqa: E731
+    i, g, r = f(init), f(got), f(ref)
+    return float(np.linalg.norm((g - i) - (r - i)) / max(np.linalg.norm(r - i), 1e-30))
+
+
+def initial_weights(model_name="debug-llama", **kw):
+    """The seeded initial weights every engine starts from (init is a function of seed + parameter name)."""
+    import torch
+
+    from distributed_training_guide_b200.engine import TrainEngine
+
+    torch.manual_seed(0)
+    eng = TrainEngine.create(model_name, parallelism="single", batch_size=1, seq_length=32, device="cpu", lr=1e-3, **kw)
+    return {k: v.detach().float().clone().numpy() for k, v in eng.model.state_dict().items()}

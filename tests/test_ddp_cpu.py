@@ -2,7 +2,7 @@
 single-process run that sees the concatenated batch."""
 import torch
 
-from dist_utils import run_distributed
+from dist_utils import initial_weights, run_distributed, update_rel_err
 
 
 def _train(rank, world, parallelism, steps, zero1):
@@ -54,6 +54,8 @@ def test_ddp_matches_single_process(parallelism):
         assert abs(0.5 * (l0[i] + l1[i]) - ref_losses[i]) < 2e-2, (i, l0[i], l1[i], ref_losses[i])
     for k in sd0:
         assert np.abs(sd0[k] - ref_sd[k].numpy()).max() < 2e-2, k
+    err = update_rel_err(initial_weights(), sd0, {k: v.numpy() for k, v in ref_sd.items()})
+    assert err < 0.1, err  # the update itself (not just the weights) matches the single-process run
 
 
 def _train_accum(rank, world, steps, K):
@@ -93,7 +95,9 @@ def test_gradient_accumulation_with_no_sync_matches_big_batch():
                 parts.append(torch.randint(0, eng.config.vocab_size, (1, 32), generator=g))
         ids = torch.cat(parts)
         eng.step({"input_ids": ids, "labels": ids.clone()})
-    ref_sd = {k: v.detach().float() for k, v in eng.model.state_dict().items()}
+    ref_sd = {k: v.detach().float().numpy() for k, v in eng.model.state_dict().items()}
     for k in sd0:
         assert np.array_equal(sd0[k], sd1[k]), k
-        assert np.abs(sd0[k] - ref_sd[k].numpy()).max() < 2e-2, k
+    # an optimizer step per micro-batch (or a dropped micro-batch) puts this at ~0.9; bf16 rounding at ~0.03
+    err = update_rel_err(initial_weights(), sd0, ref_sd)
+    assert err < 0.1, err

@@ -88,6 +88,24 @@ class GPT2Model(nn.Module):
         return self.h
 
 
+@torch.no_grad()
+def init_parameter_(p, name: str, seed: int, n_layer: int, std: float = 0.02):
+    """GPT-2 initialisation of one parameter as a pure function of (seed, name): biases 0, LayerNorm gains 1, residual
+    projections N(0, std / sqrt(2 L)), everything else N(0, std) — the same values under every parallel layout (the
+    sharded engine materialises one group at a time and keeps only its slice)."""
+    from .llama import _name_seed
+
+    if name.endswith("bias"):
+        p.zero_()
+    elif "ln_" in name:
+        p.fill_(1.0)
+    else:
+        s = std / math.sqrt(2 * n_layer) if name.endswith("c_proj.weight") else std
+        gen = torch.Generator(device=p.device)
+        gen.manual_seed(_name_seed(seed, name))
+        p.copy_(torch.empty(tuple(p.shape), dtype=torch.float32, device=p.device).normal_(0.0, s, generator=gen).to(p.dtype))
+
+
 class GPT2LMHeadModel(nn.Module):
     def __init__(self, config: ModelConfig, dtype=None, device=None):
         super().__init__()
@@ -95,7 +113,9 @@ class GPT2LMHeadModel(nn.Module):
         self.transformer = GPT2Model(config, dtype, device)
         self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False, dtype=dtype, device=device)
         self.lm_head.weight = self.transformer.wte.weight  # tied
-        self.layer_pre_hooks, self.layer_post_hooks = [], []
+        #: parallel engine (parallel/ddp.py): the same hook protocol as the Llama model — called around every block
+        #: and in front of the head so that gradient buckets are reduced as soon as they are final
+        self.engine = None
         self.activation_checkpointing = False
 
     @property
@@ -103,19 +123,14 @@ class GPT2LMHeadModel(nn.Module):
         return self.transformer
 
     @torch.no_grad()
-    def init_weights(self, std=0.02):
+    def init_weights(self, std=0.02, seed=0):
         n_layer = self.config.num_hidden_layers
+        seen = set()
         for name, p in self.named_parameters():
-            if p.is_meta:
+            if p.is_meta or id(p) in seen:
                 continue
-            if name.endswith("bias"):
-                p.zero_()
-            elif "ln_" in name:
-                p.fill_(1.0)
-            elif name.endswith("c_proj.weight"):
-                p.normal_(0.0, std / math.sqrt(2 * n_layer))
-            else:
-                p.normal_(0.0, std)
+            seen.add(id(p))
+            init_parameter_(p, name, seed, n_layer, std)
 
     def num_parameters(self):
         return sum(p.numel() for p in self.parameters())
@@ -129,14 +144,19 @@ class GPT2LMHeadModel(nn.Module):
         t = self.transformer
         if position_ids is None:
             position_ids = torch.arange(S, device=input_ids.device)
+        eng = self.engine
+        if eng is not None:
+            eng.pre_forward(self)
         x = t.wte(input_ids) + t.wpe(position_ids)
         x = F.dropout(x, t.p, self.training)
-        for blk in t.h:
-            for hook in self.layer_pre_hooks:
-                hook(blk)
+        for i, blk in enumerate(t.h):
+            if eng is not None:
+                x, _ = eng.pre_layer(i, blk, x, None)
             x = blk(x)
-            for hook in self.layer_post_hooks:
-                hook(blk)
+            if eng is not None:
+                x, _ = eng.post_layer(i, blk, x, None)
+        if eng is not None:
+            x, _ = eng.pre_head(x, None)
         logits = self.lm_head(t.ln_f(x))
         loss = self.loss_function(logits, labels) if labels is not None else None
         return SimpleNamespace(loss=loss, logits=logits)

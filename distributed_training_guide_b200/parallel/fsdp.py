@@ -34,7 +34,7 @@ import torch
 import torch.distributed as dist
 from torch.autograd import Variable
 
-from ..models.llama import FusedWeight, LlamaDecoderLayer, init_parameter_
+from ..models.llama import FusedWeight, LlamaDecoderLayer, LlamaForCausalLM, init_parameter_
 from ..ops import reference as ref
 from ..ops import join_wgrad_stream
 from ..utils.timers import nvtx_range
@@ -85,7 +85,13 @@ class FSDPEngine:
         core = model.model
         self.layers = list(core.layers)
         L = len(self.layers)
-        assert not model.config.tie_word_embeddings, "FSDP engine expects untied embeddings (Llama family)"
+        # Llama: gradients are written by the wgrad kernels (direct write, fused q|k|v / gate|up views).  Anything else
+        # (GPT-2: the reference's smoke model) gets its gradients from autograd, which ACCUMULATES into p.grad — those
+        # buffers are cleared before use — and may tie lm_head to the embedding, which then stays gathered all step.
+        self.is_llama = isinstance(model, LlamaForCausalLM)
+        self.direct_write = self.use_kernels and self.is_llama
+        self.tied = bool(getattr(model.config, "tie_word_embeddings", False))
+        assert self.is_llama or init_fn is None, "tensor-parallel slices are implemented for the Llama family"
         pad = ALIGN * world_size * 16
 
         def layout(named):
@@ -95,11 +101,22 @@ class FSDPEngine:
             return _round_up(max(off, pad), pad)
 
         layer_named = []
-        for i, layer in enumerate(self.layers):
-            named = dict(layer.named_parameters())
-            layer_named.append([(f"model.layers.{i}.{n}", named[n]) for n in LlamaDecoderLayer.FLAT_ORDER])
-        embed_named = [("model.embed_tokens.weight", core.embed_tokens.weight)]
-        head_named = [("model.norm.weight", core.norm.weight), ("lm_head.weight", model.lm_head.weight)]
+        if self.is_llama:
+            for i, layer in enumerate(self.layers):
+                named = dict(layer.named_parameters())
+                layer_named.append([(f"model.layers.{i}.{n}", named[n]) for n in LlamaDecoderLayer.FLAT_ORDER])
+            embed_named = [("model.embed_tokens.weight", core.embed_tokens.weight)]
+            head_named = [("model.norm.weight", core.norm.weight), ("lm_head.weight", model.lm_head.weight)]
+            default_init = lambda p, n: init_parameter_(p, n, seed)  # noqa: E731
+        else:
+            from ..models.gpt2 import init_parameter_ as gpt2_init
+
+            for i, layer in enumerate(self.layers):
+                layer_named.append([(f"transformer.h.{i}.{n}", p) for n, p in layer.named_parameters()])
+            embed_named = [("transformer.wte.weight", core.wte.weight), ("transformer.wpe.weight", core.wpe.weight)]
+            head_named = [(f"transformer.ln_f.{n}", p) for n, p in core.ln_f.named_parameters()]
+            assert self.tied and model.lm_head.weight is core.wte.weight, "GPT-2 layout expects a tied lm_head"
+            default_init = lambda p, n: gpt2_init(p, n, seed, L)  # noqa: E731
         max_layer = max(layout(n) for n in layer_named) if layer_named else pad
 
         def local(n):
@@ -129,14 +146,14 @@ class FSDPEngine:
                 return bufs.pop(0)[:n]
 
             g = FlatGroup(name, named, self.device, dtype, pad_multiple=pad, alloc=alloc, with_grad=True,
-                          direct_write=self.use_kernels)
+                          direct_write=self.direct_write)
             assert g.padded_numel == n_pad
             # deterministic init of the whole group inside the slot, then keep only my shard
             for n, p in named:
                 if init_fn is not None:
                     init_fn(p, n)  # tensor-parallel slices
                 else:
-                    init_parameter_(p, n, seed)
+                    default_init(p, n)
             per = g.padded_numel // world_size
             sh = symmetric(per)
             sh.copy_(g.param[rank * per:(rank + 1) * per])
@@ -151,6 +168,8 @@ class FSDPEngine:
             self.slot_of[g.name], self.gslot_of[g.name] = fs, gs
             layer = self.layers[i]
             layer._flat_group = g
+            if not self.is_llama:
+                continue
             for fname, members in LlamaDecoderLayer.FUSED.items():
                 data, grad = g.fused_view([f"model.layers.{i}.{m}" for m in members])
                 fw = FusedWeight(data, grad)
@@ -266,7 +285,7 @@ class FSDPEngine:
             self.unshard(self.layer_groups[0])
 
     def pre_forward(self, model):
-        if not self.use_kernels:  # autograd accumulates into these on the torch.distributed path
+        if not self.direct_write:  # autograd accumulates into these (torch.distributed path, non-Llama models)
             self.embed.grad.zero_()
             self.head.grad.zero_()
         self.wait_unsharded(self.embed)
@@ -274,7 +293,7 @@ class FSDPEngine:
     def pre_layer(self, i, layer, x, residual):
         g = self.layer_groups[i]
         self.wait_unsharded(g)
-        if i == 0:
+        if i == 0 and not self.tied:  # a tied lm_head needs the embedding again at the end of forward
             self.release(self.embed)
         # forward prefetch: depth 1 is FSDP2's implicit prefetch; --prefetch-layers (ch05) uses every
         # rotating slot (the slot of layer i+2 is the one layer i-1 just released)
@@ -292,6 +311,8 @@ class FSDPEngine:
 
     def pre_head(self, x, residual):
         self.wait_unsharded(self.head)
+        if self.tied:
+            self.wait_unsharded(self.embed)
         return boundary(self._post_backward_head, x, residual)
 
     # -- backward schedule ---------------------------------------------------------------------------------
@@ -321,7 +342,7 @@ class FSDPEngine:
                     t0 = self._trace_begin()
                     torch.cuda.current_stream().wait_event(ev)
                     self._trace_end("stall_grad_slot", t0)
-        else:
+        if not self.direct_write:
             g.grad.zero_()
 
     def _post_backward_layer(self, i):

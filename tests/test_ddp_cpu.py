@@ -101,3 +101,41 @@ def test_gradient_accumulation_with_no_sync_matches_big_batch():
     # an optimizer step per micro-batch (or a dropped micro-batch) puts this at ~0.9; bf16 rounding at ~0.03
     err = update_rel_err(initial_weights(), sd0, ref_sd)
     assert err < 0.1, err
+
+
+def _train_gpt2(rank, world, steps):
+    from distributed_training_guide_b200.engine import TrainEngine
+
+    torch.manual_seed(0)
+    eng = TrainEngine.create("debug-gpt2", parallelism="ddp", batch_size=2, seq_length=32, device="cpu", lr=1e-3)
+    eng.model.eval()   # dropout off: the two layouts draw different masks
+    for i in range(steps):
+        g = torch.Generator().manual_seed(1000 * i + rank)
+        ids = torch.randint(0, eng.config.vocab_size, (2, 32), generator=g)
+        eng.step({"input_ids": ids, "labels": ids.clone()})
+    return {k: v.detach().float().clone() for k, v in eng.model.state_dict().items()}
+
+
+def test_gpt2_under_ddp_matches_single_process():
+    """The reference's canonical multi-GPU smoke model: tied embeddings, LayerNorm, biases — gradients come from
+    autograd (PyTorch ops), the buckets and the sharded optimizer are the same engine as for Llama."""
+    import numpy as np
+
+    from distributed_training_guide_b200.engine import TrainEngine
+
+    steps, world = 3, 2
+    sd0, sd1 = run_distributed(_train_gpt2, world=world, args=(steps,))
+    torch.manual_seed(0)
+    eng = TrainEngine.create("debug-gpt2", parallelism="single", batch_size=4, seq_length=32, device="cpu", lr=1e-3)
+    eng.model.eval()
+    init = {k: v.detach().float().clone().numpy() for k, v in eng.model.state_dict().items()}
+    for i in range(steps):
+        parts = [torch.randint(0, eng.config.vocab_size, (2, 32), generator=torch.Generator().manual_seed(1000 * i + r))
+                 for r in range(world)]
+        ids = torch.cat(parts)
+        eng.step({"input_ids": ids, "labels": ids.clone()})
+    ref_sd = {k: v.detach().float().numpy() for k, v in eng.model.state_dict().items()}
+    for k in sd0:
+        assert np.array_equal(sd0[k], sd1[k]), k                     # replicas stay identical
+    err = update_rel_err(init, sd0, ref_sd)
+    assert err < 0.1, err                                            # and they actually trained, like one process

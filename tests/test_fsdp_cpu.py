@@ -146,3 +146,42 @@ def test_fsdp_gradient_accumulation_matches_big_batch():
     # an optimizer step per micro-batch (or a dropped micro-batch) puts this at ~0.9; bf16 rounding at ~0.03
     err = update_rel_err(initial_weights(), sd0, ref_sd)
     assert err < 0.1, err
+
+
+def _fsdp_gpt2(rank, world, steps):
+    from distributed_training_guide_b200.engine import TrainEngine
+
+    torch.manual_seed(0)
+    eng = TrainEngine.create("debug-gpt2", parallelism="fsdp", batch_size=2, seq_length=32, device="cpu", lr=1e-3)
+    eng.model.eval()   # dropout off: sharded and single-process runs draw different masks
+    init = {k: v.detach().float().clone() for k, v in eng.strategy.engine.full_state_dict().items()}
+    for i in range(steps):
+        g = torch.Generator().manual_seed(1000 * i + rank)
+        ids = torch.randint(0, eng.config.vocab_size, (2, 32), generator=g)
+        eng.step({"input_ids": ids, "labels": ids.clone()})
+    return init, {k: v.detach().float().clone() for k, v in eng.strategy.engine.full_state_dict().items()}
+
+
+def test_gpt2_under_fsdp_matches_single_process():
+    """GPT-2 (tied lm_head, biases, LayerNorm; gradients from autograd) through the sharded engine: the reference's
+    smoke model for its FSDP chapter."""
+    from distributed_training_guide_b200.engine import TrainEngine
+
+    steps, world = 3, 2
+    (init0, sd0), (init1, sd1) = run_distributed(_fsdp_gpt2, world=world, args=(steps,))
+    torch.manual_seed(0)
+    eng = TrainEngine.create("debug-gpt2", parallelism="single", batch_size=4, seq_length=32, device="cpu", lr=1e-3)
+    eng.model.eval()
+    ref_init = {k: v.detach().float().clone().numpy() for k, v in eng.model.state_dict().items()}
+    for k in init0:   # same seed -> the sharded build materialises exactly the single-process weights
+        assert np.array_equal(init0[k], ref_init[k]), k
+    for i in range(steps):
+        parts = [torch.randint(0, eng.config.vocab_size, (2, 32), generator=torch.Generator().manual_seed(1000 * i + r))
+                 for r in range(world)]
+        ids = torch.cat(parts)
+        eng.step({"input_ids": ids, "labels": ids.clone()})
+    ref_sd = {k: v.detach().float().numpy() for k, v in eng.model.state_dict().items() if k in sd0}
+    for k in sd0:
+        assert np.array_equal(sd0[k], sd1[k]), k
+    err = update_rel_err({k: ref_init[k] for k in ref_sd}, sd0, ref_sd)
+    assert err < 0.1, err

@@ -245,6 +245,7 @@ class LlamaForCausalLM(nn.Module):
         vocab_local = config.vocab_size // tp_size  # vocabulary-sharded head (loss-parallel)
         self.lm_head = Linear(config.hidden_size, vocab_local, dtype, device)
         if config.tie_word_embeddings:
+            assert tp_size == 1, "tied embeddings cannot be tensor-parallel (vocabulary- vs hidden-sharded)"
             self.lm_head.weight = self.model.embed_tokens.weight
         #: parallel engine (parallel/ddp.py, fsdp.py): called around every decoder layer and the
         #: head so it can insert autograd boundaries, prefetch shards and launch bucket kernels

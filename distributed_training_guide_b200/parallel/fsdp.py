@@ -106,7 +106,9 @@ class FSDPEngine:
                 named = dict(layer.named_parameters())
                 layer_named.append([(f"model.layers.{i}.{n}", named[n]) for n in LlamaDecoderLayer.FLAT_ORDER])
             embed_named = [("model.embed_tokens.weight", core.embed_tokens.weight)]
-            head_named = [("model.norm.weight", core.norm.weight), ("lm_head.weight", model.lm_head.weight)]
+            head_named = [("model.norm.weight", core.norm.weight)]
+            if not self.tied:  # a tied lm_head IS the embedding parameter (it lives in the embed group)
+                head_named.append(("lm_head.weight", model.lm_head.weight))
             default_init = lambda p, n: init_parameter_(p, n, seed)  # noqa: E731
         else:
             from ..models.gpt2 import init_parameter_ as gpt2_init

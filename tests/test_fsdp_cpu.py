@@ -1,5 +1,6 @@
 """FSDP engine schedule on CPU (gloo, 2 processes) vs a single-process run on the concatenated batch."""
 import numpy as np
+import pytest
 import torch
 
 from dist_utils import initial_weights, run_distributed, update_rel_err
@@ -184,4 +185,47 @@ def test_gpt2_under_fsdp_matches_single_process():
     for k in sd0:
         assert np.array_equal(sd0[k], sd1[k]), k
     err = update_rel_err({k: ref_init[k] for k in ref_sd}, sd0, ref_sd)
+    assert err < 0.1, err
+
+
+def _tied_llama(rank, world, model_dir, parallelism, steps):
+    from distributed_training_guide_b200.engine import TrainEngine
+
+    torch.manual_seed(0)
+    eng = TrainEngine.create(model_dir, parallelism=parallelism, batch_size=2, seq_length=32, device="cpu", lr=1e-3)
+    for i in range(steps):
+        g = torch.Generator().manual_seed(1000 * i + rank)
+        ids = torch.randint(0, eng.config.vocab_size, (2, 32), generator=g)
+        eng.step({"input_ids": ids, "labels": ids.clone()})
+    sd = eng.strategy.engine.full_state_dict() if parallelism == "fsdp" else eng.model.state_dict()
+    return {k: v.detach().float().clone() for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("parallelism", ["ddp", "fsdp"])
+def test_llama_with_tied_embeddings(tmp_path, parallelism):
+    """Llama-3.2-style tie_word_embeddings: the lm_head and the embedding are one parameter living in the embed group."""
+    import json
+
+    from distributed_training_guide_b200.engine import TrainEngine
+    from distributed_training_guide_b200.models import get_config
+    from distributed_training_guide_b200.models.configs import to_hf_config_dict
+
+    d = to_hf_config_dict(get_config("debug-llama"))
+    d["tie_word_embeddings"] = True
+    (tmp_path / "config.json").write_text(json.dumps(d))
+    steps, world = 2, 2
+    sd0, sd1 = run_distributed(_tied_llama, world=world, args=(str(tmp_path), parallelism, steps))
+    torch.manual_seed(0)
+    eng = TrainEngine.create(str(tmp_path), parallelism="single", batch_size=4, seq_length=32, device="cpu", lr=1e-3)
+    assert eng.model.lm_head.weight is eng.model.model.embed_tokens.weight
+    init = {k: v.detach().float().clone().numpy() for k, v in eng.model.state_dict().items()}
+    for i in range(steps):
+        parts = [torch.randint(0, eng.config.vocab_size, (2, 32), generator=torch.Generator().manual_seed(1000 * i + r))
+                 for r in range(world)]
+        ids = torch.cat(parts)
+        eng.step({"input_ids": ids, "labels": ids.clone()})
+    ref_sd = {k: v.detach().float().numpy() for k, v in eng.model.state_dict().items() if k in sd0}
+    for k in sd0:
+        assert np.array_equal(sd0[k], sd1[k]), k
+    err = update_rel_err({k: init[k] for k in ref_sd}, sd0, ref_sd)
     assert err < 0.1, err

@@ -448,10 +448,13 @@ class TwoDParallel(Strategy):
     local_engine = None
 
     def grad_sync(self, model, enabled=True):
+        self._boundary = enabled  # read by backward() on the engine-less path (DTG_TP_OVERLAP_OPT=0)
         eng = self.engine if self.engine is not None else self.local_engine
         if enabled or eng is None or not hasattr(eng, "no_sync"):
             return contextlib.nullcontext()
         return eng.no_sync()
+
+    _boundary = True
 
     def pre_step(self, model):
         if self.engine is not None:
@@ -459,8 +462,10 @@ class TwoDParallel(Strategy):
 
     def backward(self, model, loss):
         loss.backward()
-        if self.engine is None and self.local_engine is None:
-            for g in self.groups:  # pure TP: fix up the replicated gradients before the optimizer runs
+        if self.engine is None and self.local_engine is None and self._boundary:
+            # pure TP without the in-backward optimizer: sum the replicated (norm-gain) gradients over the tp group
+            # once per optimizer step — on the boundary micro-batch, after local accumulation
+            for g in self.groups:
                 self._sync_replicated(g)
 
     def save_checkpoint(self, exp_dir, model, optimizer, lr_scheduler, state):

@@ -48,6 +48,10 @@ class TPContext:
         self.max_tokens = max_tokens
         assert max_tokens % tp_size == 0
         self.rpp = max_tokens // tp_size  # rows (tokens) per rank
+        if self.use_kernels and tp_size > 1 and self.rpp % 256 != 0:
+            raise ValueError(
+                f"tensor parallelism: tokens per rank = batch x seq / tp = {max_tokens} / {tp_size} = {self.rpp} must be "
+                "a multiple of 256 (one CTA-pair row tile of the fused all-gather -> GEMM kernel); raise -b or -s")
         self.n_layers = n_layers
         if self.use_kernels:
             import os

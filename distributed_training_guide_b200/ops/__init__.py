@@ -293,12 +293,13 @@ def attention_qkv(qkv, nh, nkv, scale=None):
     """Causal self-attention. qkv: [B,S,nh+2*nkv,d] (q heads | k heads | v heads) -> [B,S,nh,d]."""
     d = qkv.shape[-1]
     scale = scale if scale is not None else 1.0 / math.sqrt(d)
-    if _ext.use_cuda_kernel("attention", qkv) and qkv.dtype == torch.bfloat16 and d == 128:
+    if _ext.use_cuda_kernel("attention", qkv) and qkv.dtype == torch.bfloat16 and d == 128 and qkv.shape[1] % 128 == 0:
         return _AttentionQKV.apply(qkv, nh, nkv, scale)
     q, k, v = qkv[:, :, :nh], qkv[:, :, nh:nh + nkv], qkv[:, :, nh + nkv:]
     if qkv.is_cuda:
-        # head dims other than 128 (GPT-2 style / toy configs) are outside the sm_100a kernel's
-        # scope; use the library kernel rather than the O(S^2)-memory reference
+        # head dims other than 128 (GPT-2 style / toy configs) and sequence lengths that are not a multiple of
+        # the 128-row tile are outside the sm_100a kernel's scope; use the library kernel rather than the
+        # O(S^2)-memory reference
         o = torch.nn.functional.scaled_dot_product_attention(
             q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=True, scale=scale,
             enable_gqa=(nh != nkv))

@@ -201,8 +201,19 @@ class DataParallelZero1(Strategy):
         with self.data_guard():
             _load_pretrained(args, model=model)
         if env.distributed and env.world_size > 1:
-            for g in self.groups:  # replicas must start identical (torch DDP broadcasts in its ctor, N1)
-                dist.broadcast(g.param, src=0)
+            # Replicas must start identical.  torch DDP broadcasts rank 0's parameters in its constructor (13.5 GB for
+            # a 7B model); here the weights are a pure function of (seed, parameter name), so the
+            # replicas already agree and a checksum per group is enough — the broadcast is kept as the repair path.
+            sums = torch.stack([g.param.float().sum() for g in self.groups])
+            ref = sums.clone()
+            dist.broadcast(ref, src=0)
+            if not torch.equal(sums, ref):
+                LOGGER.warning("replica differs from rank 0 after initialisation; broadcasting rank 0's parameters")
+            flag = torch.tensor([0.0 if torch.equal(sums, ref) else 1.0], device=sums.device)
+            dist.all_reduce(flag)
+            if float(flag.item()) > 0:
+                for g in self.groups:
+                    dist.broadcast(g.param, src=0)
         self.model = model
         return model
 

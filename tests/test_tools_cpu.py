@@ -42,3 +42,13 @@ def test_download_helper_falls_back_to_embedded_config():
                         "meta-llama/Llama-3.1-405B", "--skip-model"], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stderr
     assert "405.85 B parameters" in r.stdout or "cached" in r.stdout, r.stdout
+
+
+def test_bench_watchdog_dumps_stacks_and_exits():
+    """bench.py arms a watchdog per stage: a stage that stalls past its budget dumps every thread's stack and exits
+    instead of hanging until the caller's limit."""
+    code = ("import sys, time; sys.path.insert(0, %r); import bench; bench._stage('stalling stage', budget_s=1); "
+            "time.sleep(30)") % str(ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0
+    assert "stalling stage" in r.stderr and "Timeout (0:00:01)" in r.stderr and "time.sleep" not in r.stdout

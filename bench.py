@@ -160,6 +160,9 @@ def run_b200(args):
     h2d_bytes = sum(v.numel() * v.element_size() for v in host_batches[0].values())
 
     eng.phase_timing = bool(os.environ.get("DTG_PHASE_TIMING"))
+    ddp_engine = getattr(eng.model, "engine", None)
+    if world > 1 and hasattr(ddp_engine, "measure_tail"):
+        ddp_engine.measure_tail = True   # two CUDA events per step: exposed communication = comm stream past backward
     _stage(f"engine ready; {args.warmup} warm-up steps", budget_s=300)
     for i in range(args.warmup):
         eng.step(dev_batches[i])
@@ -234,6 +237,8 @@ def run_b200(args):
         "e2e": {"value": 1000.0 * tokens / ms_e2e, "unit": "tokens/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
+        **({"exposed_comm_ms": ddp_engine.exposed_comm_ms(last_steps=2 * args.steps)}
+           if world > 1 and hasattr(ddp_engine, "exposed_comm_ms") else {}),
         "final_loss": last,
         **({"phases_ms": eng.phase_times_ms(last_n=args.steps)} if eng.phase_timing else {}),
         **({"comm_trace": eng.model.engine.comm_trace_summary(last_steps=args.steps)}

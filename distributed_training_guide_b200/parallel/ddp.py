@@ -83,6 +83,7 @@ class DataParallelEngine:
         model.engine = self
         optimizer.external_step = self._optimizer_step
         self._pending = []  # buckets reduced this step (for the CPU fallback's deferred update)
+        self.measure_tail, self._tails = False, []  # bench.py: two events per step -> exposed_comm_ms()
         # DTG_COMM_TRACE=1: CUDA events around every bucket kernel (see comm_trace_summary)
         self.trace = [] if (self.use_kernels and os.environ.get("DTG_COMM_TRACE")) else None
 
@@ -130,6 +131,13 @@ class DataParallelEngine:
             self._launch(g)  # the embedding gradient is only complete at the very end of backward
         if self.use_kernels:
             self._done.record(self.comm_stream)
+            if self.measure_tail:
+                # exposed communication: how long the communication stream runs past the end of backward
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                d = torch.cuda.Event(enable_timing=True)
+                d.record(self.comm_stream)
+                self._tails.append((e, d))
             if self.trace is not None:
                 e = torch.cuda.Event(enable_timing=True)
                 e.record()  # end of backward on the compute stream
@@ -155,6 +163,15 @@ class DataParallelEngine:
                 self.trace.append((g.name, t0, t1))
                 return
             self._run_bucket(g, gbuf)
+
+    def exposed_comm_ms(self, last_steps=None):
+        """Mean time per step the communication stream kept running after backward had finished on the compute
+        stream (the part of the bucket kernels that is NOT hidden under backward); None if not measured."""
+        tails = self._tails[-last_steps:] if last_steps else self._tails
+        if not tails:
+            return None
+        torch.cuda.synchronize()
+        return sum(max(0.0, a.elapsed_time(b)) for a, b in tails) / len(tails)
 
     def comm_trace_summary(self, last_steps=None):
         """{"bucket_ms": mean device time per bucket kernel, "sum_ms": per step, "tail_ms": how long the

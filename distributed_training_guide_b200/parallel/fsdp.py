@@ -9,9 +9,11 @@ explicit forward/backward prefetch (``05:148-161``).  torch FSDP2 runs, per grou
 ``reduce_scatter_tensor`` -> cast, then a separate fused AdamW over DTensor shards.
 
 Here each group (embedding, every decoder layer, head) is one flat parameter:
-  * the 1/N shard of every rank lives in a symmetric buffer; UNSHARD = one pull kernel that reads the
-    N shards over NVLink straight into a rotating "full" slot the layer's parameter views point at
-    (no copy-in/copy-out; ``comm.cu: allgather_kernel``), prefetched one layer ahead on a side stream;
+  * the 1/N shard of every rank lives in a symmetric buffer; UNSHARD = a one-warp device barrier plus N
+    peer-to-peer copies on the copy engines (``comm.cu: comm_allgather_ce``; the SM pull kernel
+    ``allgather_kernel`` is kept behind ``DTG_FSDP_AG=sm``) straight into a rotating "full" slot the layer's
+    parameter views point at — no copy-in/copy-out and no SM time — prefetched one or two layers ahead on a
+    side stream;
   * gradients are written by the wgrad GEMMs into a rotating symmetric "grad" slot; when the
     layer's backward boundary fires, ONE kernel reduce-scatters the slot (pull + fp32 sum),
     applies AdamW to this rank's shard of parameters and optimizer state, and leaves the updated

@@ -239,7 +239,7 @@ class DataParallelZero1(Strategy):
 
 
 class FullyShardedDataParallel(Strategy):
-    """Chapters 04 / 05: ZeRO-3 over the data-parallel group with NVLink pull-unshard and the fused
+    """Chapters 04 / 05: ZeRO-3 over the data-parallel group with the NVLink copy-engine unshard and the fused
     reduce-scatter + AdamW kernel (``parallel/fsdp.py``); meta-device construction, optional CPU
     offload of the optimizer, activation checkpointing and explicit prefetch flags."""
 

@@ -12,6 +12,7 @@ import math
 from types import SimpleNamespace
 
 import torch
+import torch.utils.checkpoint
 import torch.nn.functional as F
 from torch import nn
 
@@ -152,7 +153,12 @@ class GPT2LMHeadModel(nn.Module):
         for i, blk in enumerate(t.h):
             if eng is not None:
                 x, _ = eng.pre_layer(i, blk, x, None)
-            x = blk(x)
+            if self.activation_checkpointing and torch.is_grad_enabled():
+                # --checkpoint-activations: keep only the block input, re-run the block in backward (the
+                # RNG state is restored for the replay, so dropout masks match)
+                x = torch.utils.checkpoint.checkpoint(blk, x, use_reentrant=False)
+            else:
+                x = blk(x)
             if eng is not None:
                 x, _ = eng.post_layer(i, blk, x, None)
         if eng is not None:

@@ -55,3 +55,23 @@ def test_trainer_uses_native_loader(tmp_path):
     assert isinstance(dl, D.NativeTokenLoader) and len(dl) == 10
     batch = next(iter(dl))
     assert batch["input_ids"].shape == (4, 64) and batch["input_ids"].max() < cfg.vocab_size
+
+
+def test_token_loader_restarts_and_teardown(tmp_path):
+    """Abandoning an epoch half way (set_epoch while the producer thread is ahead) and destroying a loader whose
+    producer is mid-epoch must neither deadlock nor crash."""
+    C = _ext.load(True)
+    S, B = 64, 4
+    toks = (np.arange(S * 997) % 50000).astype(np.uint16)
+    path = tmp_path / "stress.bin"
+    toks.tofile(path)
+    ld = C.TokenLoader(str(path), 2, S, B, 0, 2, 3, 4, False)
+    for ep in range(60):
+        ld.set_epoch(ep)
+        n = ld.num_batches()
+        for _ in range(n if ep % 3 else n // 2):
+            b = ld.next()
+            assert b.shape == (B, S)
+    ld2 = C.TokenLoader(str(path), 2, S, B, 1, 2, 3, 4, False)
+    ld2.next()
+    del ld2

@@ -33,7 +33,7 @@ def test_toy_resumes_from_state_file(tmp_path):
 
 def test_toy_injected_failure_restarts(tmp_path):
     try:
-        r = _launch(tmp_path, ["--steps", "20", "--fail-at-steps", "7"], 150)
+        r = _launch(tmp_path, ["--steps", "20", "--fail-at-steps", "7"], 75)
     except subprocess.TimeoutExpired:
         pytest.skip("gloo re-rendezvous after a torchrun restart is slow on this host")
     out = r.stdout + r.stderr

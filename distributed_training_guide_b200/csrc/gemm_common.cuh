@@ -52,7 +52,7 @@ struct GemmDist {
 };
 
 #ifdef __CUDACC__
-__device__ __forceinline__ int tile_m(int t, int num_m_tiles, const GemmDist& d) {
+__host__ __device__ __forceinline__ int tile_m(int t, int num_m_tiles, const GemmDist& d) {
   int m = t % num_m_tiles + d.m_tile_shift;
   return m >= num_m_tiles ? m - num_m_tiles : m;
 }
@@ -63,13 +63,14 @@ __device__ __forceinline__ int tile_m(int t, int num_m_tiles, const GemmDist& d)
 // With an in-kernel all-gather
 // (`local_m_tiles` > 0): first every tile of my own rows (pure local work while the communication CTAs
 // fetch), then the remote row tiles in the order they are being fetched.
-__device__ __forceinline__ void tile_mn(int t, int num_m_tiles, const GemmDist& d, int local_m_tiles, int& m, int& n) {
+__host__ __device__ __forceinline__ void tile_mn(int t, int num_m_tiles, const GemmDist& d, int local_m_tiles, int& m, int& n) {
   if (local_m_tiles <= 0) {
     if (d.group_m > 0 && d.group_m < num_m_tiles) {
       const int per_group = d.group_m * d.num_n_tiles;
       const int g = t / per_group, r = t - g * per_group;
       const int m0 = g * d.group_m;
-      const int gsz = min(d.group_m, num_m_tiles - m0);
+      const int rest_m = num_m_tiles - m0;
+      const int gsz = d.group_m < rest_m ? d.group_m : rest_m;
       m = m0 + r % gsz;
       n = r / gsz;
       return;

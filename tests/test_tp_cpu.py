@@ -57,3 +57,57 @@ def test_2d_parallel_matches_single_process():
     # tensor-parallel peers of one replica agree exactly on the loss
     for dp_rank, lst in by_dp.items():
         assert np.allclose(lst[0], lst[1], atol=1e-5)
+
+
+def _train_accum(rank, world, parallelism, tp, steps, K):
+    """K micro-batches per optimizer step (the SAME micro-batches every step, so the losses fall and expose a wrong
+    update), through the strategy's grad_sync() like trainer.py does."""
+    from distributed_training_guide_b200.engine import TrainEngine
+
+    torch.manual_seed(0)
+    eng = TrainEngine.create("debug-llama-tp", parallelism=parallelism, batch_size=1, seq_length=32, device="cpu",
+                             lr=3e-3, tensor_parallel=tp, num_layers=2)
+    s = eng.strategy
+    losses = []
+    for _ in range(steps):
+        tot = 0.0
+        for m in range(K):
+            g = torch.Generator().manual_seed(100 * m + s.dp_rank)
+            ids = torch.randint(0, eng.config.vocab_size, (1, 32), generator=g)
+            s.pre_step(eng.model)
+            out = eng.model(**s.prepare_batch({"input_ids": ids, "labels": ids.clone()}))
+            with s.grad_sync(eng.model, enabled=(m == K - 1)):
+                s.backward(eng.model, out.loss / K)
+            tot += float(out.loss) / K
+        eng.optimizer.step()
+        eng.lr_scheduler.step()
+        eng.optimizer.zero_grad()
+        losses.append(tot)
+    return losses, s.dp_rank, s.dp_size
+
+
+def _single_accum_reference(steps, K, dp):
+    from distributed_training_guide_b200.engine import TrainEngine
+
+    torch.manual_seed(0)
+    eng = TrainEngine.create("debug-llama-tp", parallelism="single", batch_size=K * dp, seq_length=32, device="cpu",
+                             lr=3e-3, num_layers=2)
+    parts = [torch.randint(0, eng.config.vocab_size, (1, 32), generator=torch.Generator().manual_seed(100 * m + r))
+             for m in range(K) for r in range(dp)]
+    ids = torch.cat(parts)
+    return [float(eng.step({"input_ids": ids, "labels": ids.clone()})) for _ in range(steps)]
+
+
+def test_gradient_accumulation_under_tp_and_2d():
+    steps, K = 5, 2
+    ref1 = _single_accum_reference(steps, K, dp=1)
+    assert ref1[0] - ref1[-1] > 0.3, ref1            # the repeated data is being learnt: the check below has teeth
+    for losses, _, _ in run_distributed(_train_accum, world=2, args=("tp", 2, steps, K)):
+        assert max(abs(a - b) for a, b in zip(losses, ref1)) < 0.05, (losses, ref1)
+    ref2 = _single_accum_reference(steps, K, dp=2)
+    res = run_distributed(_train_accum, world=4, args=("2d", 2, steps, K), timeout=600)
+    by_dp = {}
+    for losses, dp_rank, _ in res:
+        by_dp.setdefault(dp_rank, losses)
+    mean = [0.5 * (a + b) for a, b in zip(by_dp[0], by_dp[1])]
+    assert max(abs(a - b) for a, b in zip(mean, ref2)) < 0.05, (mean, ref2)

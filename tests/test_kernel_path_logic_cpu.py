@@ -6,6 +6,7 @@ from types import SimpleNamespace
 from unittest import mock
 
 import numpy as np
+import pytest
 import torch
 
 from dist_utils import update_rel_err
@@ -80,15 +81,16 @@ def _patches():
             mock.patch("torch.cuda.synchronize", lambda *a, **k: None)]
 
 
-def _run(engine_kind, kernel_path, K, steps=3):
+def _run(engine_kind, kernel_path, K, steps=3, model_name="debug-llama"):
     from distributed_training_guide_b200.engine import TrainEngine
 
     with contextlib.ExitStack() as es:
         for p in _patches():
             es.enter_context(p)
         torch.manual_seed(0)
-        eng = TrainEngine.create("debug-llama", parallelism=engine_kind, batch_size=2, seq_length=32, device="cpu",
+        eng = TrainEngine.create(model_name, parallelism=engine_kind, batch_size=2, seq_length=32, device="cpu",
                                  lr=1e-3)
+        eng.model.eval()
         e = eng.strategy.engine
         init = {k: v.detach().float().clone().numpy() for k, v in eng.model.state_dict().items()}
         fake = _FakeSymm()
@@ -118,17 +120,20 @@ def _run(engine_kind, kernel_path, K, steps=3):
         return init, {k: v.detach().float().clone().numpy() for k, v in sd.items()}, fake.calls
 
 
-def test_fsdp_kernel_branch_matches_fallback_branch():
+@pytest.mark.parametrize("model_name", ["debug-llama", "debug-gpt2"])
+def test_fsdp_kernel_branch_matches_fallback_branch(model_name):
     for K in (1, 2):
-        init, want, _ = _run("fsdp", False, K)
-        _, got, calls = _run("fsdp", True, K)
+        init, want, _ = _run("fsdp", False, K, model_name=model_name)
+        _, got, calls = _run("fsdp", True, K, model_name=model_name)
         assert "allgather" in calls and ("rs_adamw" in calls if K == 1 else "reduce_scatter" in calls), calls
         assert update_rel_err(init, got, want) < 0.05, K
         assert all(np.isfinite(v).all() for v in got.values())
 
 
-def test_single_gpu_engine_kernel_branch_matches_plain_optimizer():
-    """Chapter 01 on a GPU runs AdamW per bucket inside backward (the N = 1 case of the ZeRO-1 bucket kernel)."""
+@pytest.mark.parametrize("model_name", ["debug-llama", "debug-gpt2"])
+def test_single_gpu_engine_kernel_branch_matches_plain_optimizer(model_name):
+    """Chapter 01 on a GPU runs AdamW per bucket inside backward (the N = 1 case of the ZeRO-1 bucket kernel); GPT-2
+    takes the same route with autograd-accumulated gradients and a tied lm_head."""
     from distributed_training_guide_b200.engine import TrainEngine
     from distributed_training_guide_b200.parallel.ddp import DataParallelEngine
 
@@ -137,7 +142,8 @@ def test_single_gpu_engine_kernel_branch_matches_plain_optimizer():
             for p in _patches():
                 es.enter_context(p)
             torch.manual_seed(0)
-            eng = TrainEngine.create("debug-llama", parallelism="single", batch_size=2, seq_length=32, device="cpu", lr=1e-3)
+            eng = TrainEngine.create(model_name, parallelism="single", batch_size=2, seq_length=32, device="cpu", lr=1e-3)
+            eng.model.eval()  # GPT-2: no dropout, the two runs must see the same function
             init = {k: v.detach().float().clone().numpy() for k, v in eng.model.state_dict().items()}
             fake = _FakeSymm()
             if kernel_path:

@@ -131,9 +131,12 @@ def _stage(msg, budget_s=None):
     rank = os.environ.get("RANK", "0")
     if rank == "0" or os.environ.get("DTG_BENCH_VERBOSE"):
         print(f"[bench rank {rank} +{time.time() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
-    faulthandler.cancel_dump_traceback_later()
-    if budget_s:
-        faulthandler.dump_traceback_later(budget_s, exit=True)
+    try:
+        faulthandler.cancel_dump_traceback_later()
+        if budget_s:
+            faulthandler.dump_traceback_later(budget_s, exit=True, file=sys.__stderr__)
+    except Exception:  # stderr without a file descriptor (captured): run without the watchdog
+        pass
 
 
 def run_b200(args):

@@ -58,3 +58,35 @@ def test_bench_prints_the_contract_json(capsys):
     assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert line["value"] > 0 and line["ms_per_step"] > 0 and line["config"]["global_batch"] == 2
     assert abs(line["value"] - 1000.0 * 2 * 64 / line["ms_per_step"]) < 1e-6 * line["value"]
+
+
+def _bench_rank(rank, world):
+    import io
+
+    import bench
+
+    args = SimpleNamespace(gpus=world, steps=2, warmup=3, impl="b200", model="debug-llama", seq_len=64, batch=1,
+                           parallelism="ddp", tensor_parallel=None, layers=None)
+    buf = io.StringIO()
+    with contextlib.ExitStack() as es:
+        for p in [mock.patch("torch.cuda.Event", _Ev), mock.patch("torch.cuda.synchronize", lambda *a, **k: None),
+                  mock.patch("torch.cuda.max_memory_allocated", lambda *a, **k: 0)]:
+            es.enter_context(p)
+        with contextlib.redirect_stdout(buf):
+            bench.run_b200(args)
+    import faulthandler
+
+    faulthandler.cancel_dump_traceback_later()
+    lines = [l for l in buf.getvalue().splitlines() if l.startswith("{")]
+    return lines[-1] if lines else ""
+
+
+def test_bench_two_ranks_prints_one_line_with_whole_job_tokens():
+    from dist_utils import run_distributed
+
+    r0, r1 = run_distributed(_bench_rank, world=2, timeout=300)
+    assert r1 == ""                                   # only rank 0 prints
+    line = json.loads(r0)
+    assert line["n_gpus"] == 2 and line["config"]["global_batch"] == 2 and "dp2" in line["config"]["parallelism"]
+    assert abs(line["value"] - 1000.0 * 2 * 64 / line["ms_per_step"]) < 1e-6 * line["value"]   # whole-job aggregate
+    assert "exposed_comm_ms" in line

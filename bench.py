@@ -140,7 +140,7 @@ def _stage(msg, budget_s=None):
 
 
 def run_b200(args):
-    _stage("importing torch", budget_s=600)
+    _stage("importing torch", budget_s=1800)
     import torch
 
     from distributed_training_guide_b200 import _ext
@@ -149,7 +149,7 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun for N>1"
     par = args.parallelism if world > 1 else "single"
-    _stage(f"building the {par} engine on {world} GPU(s) (process group, NVLink symmetric memory, model)", budget_s=600)
+    _stage(f"building the {par} engine on {world} GPU(s) (process group, NVLink symmetric memory, model)", budget_s=1800)
     eng = TrainEngine.create(args.model, parallelism=par, batch_size=args.batch, seq_length=args.seq_len,
                              tensor_parallel=args.tensor_parallel, num_layers=args.layers)
     dev = eng.device
@@ -166,7 +166,7 @@ def run_b200(args):
     ddp_engine = getattr(eng.model, "engine", None)
     if world > 1 and hasattr(ddp_engine, "measure_tail"):
         ddp_engine.measure_tail = True   # two CUDA events per step: exposed communication = comm stream past backward
-    _stage(f"engine ready; {args.warmup} warm-up steps", budget_s=300)
+    _stage(f"engine ready; {args.warmup} warm-up steps", budget_s=900)
     for i in range(args.warmup):
         eng.step(dev_batches[i])
     torch.cuda.synchronize(dev)
@@ -192,7 +192,7 @@ def run_b200(args):
     elif os.environ.get("DTG_CPU_PROFILE"):
         eng.step(dev_batches[args.warmup])
     # ---- region 1: device-timed steps, batch resident on the GPU --------------------------------
-    _stage(f"timing {args.steps} steps (device events)", budget_s=300)
+    _stage(f"timing {args.steps} steps (device events)", budget_s=900)
     _barrier_sync(dev)
     l0 = _ext.launch_count()
     with ClockSampler(dev.index or 0) as clocks:
@@ -205,7 +205,7 @@ def run_b200(args):
     launches = _ext.launch_count() - l0
     ms_dev = _dist_max(s.elapsed_time(e), dev) / args.steps
     # ---- region 2: end to end through the public API: pinned H2D every step + loss D2H every step ---
-    _stage(f"timing {args.steps} steps end to end (pinned H2D + loss D2H every step)", budget_s=300)
+    _stage(f"timing {args.steps} steps end to end (pinned H2D + loss D2H every step)", budget_s=900)
     eng.step(host_batches[args.steps])
     _barrier_sync(dev)
     s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -250,7 +250,7 @@ def run_b200(args):
     }
     if rank == 0:
         print(json.dumps(out), flush=True)
-    _stage("done; tearing down", budget_s=120)
+    _stage("done; tearing down", budget_s=300)
     eng.close()
     from distributed_training_guide_b200.parallel.bootstrap import shutdown
 

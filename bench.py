@@ -120,27 +120,61 @@ def _barrier_sync(device):
 
 
 _T0 = time.time()
+_WATCH = {"deadline": None, "stage": "", "thread": None}
+# Stage budgets (seconds).  Their SUM stays below the driver's per-N limit, so a wedged run always leaves a
+# diagnosis (stacks + signal-pad state) and exits by itself instead of being killed silently from outside.
+BUDGET = {"import": 200, "build": 200, "warmup": 100, "timed": 100, "e2e": 100, "teardown": 60}
+for _kv in filter(None, os.environ.get("DTG_BENCH_BUDGET", "").split(",")):  # e.g. "build=90,warmup=40" (debug sessions)
+    BUDGET[_kv.split("=")[0]] = int(_kv.split("=")[1])
 
 
-def _stage(msg, budget_s=None):
-    """Progress line on stderr (every rank prefixes its RANK) and, with ``budget_s``, a watchdog: if the next stage
-    does not report within that many seconds, every thread's stack is dumped to stderr and the process exits, so a
-    wedged run leaves a diagnosis instead of sitting until the caller's limit kills it."""
+def _post_mortem(stage):
+    """Runs on the watchdog thread when a stage overran: every thread's Python stack, then (best effort, on a side
+    stream so it works while a kernel is spinning) the NVLink signal-pad state of every live symmetric group."""
     import faulthandler
 
     rank = os.environ.get("RANK", "0")
+    sys.stderr.write(f"[bench rank {rank}] WATCHDOG: stage '{stage}' exceeded its budget; dumping stacks and exiting\n")
+    sys.stderr.flush()
+    try:
+        faulthandler.dump_traceback(file=sys.__stderr__, all_threads=True)
+    except Exception:
+        pass
+    try:
+        symm = sys.modules.get("distributed_training_guide_b200.parallel.symm")  # only if the engine got that far
+        for line in (symm.post_mortem(timeout_s=5.0) if symm is not None else []):
+            sys.stderr.write(f"[bench rank {rank}] {line}\n")
+    except Exception as e:  # pragma: no cover - diagnostics only
+        sys.stderr.write(f"[bench rank {rank}] (no signal-pad state: {e!r})\n")
+    sys.stderr.flush()
+    os._exit(3)
+
+
+def _watch_loop():
+    while True:
+        time.sleep(0.5)
+        d = _WATCH["deadline"]
+        if d is not None and time.time() > d:
+            _post_mortem(_WATCH["stage"])
+
+
+def _stage(msg, budget_s=None):
+    """Progress line on stderr (rank 0, or every rank with DTG_BENCH_VERBOSE=1) and, with ``budget_s``, a watchdog:
+    if the next stage does not report within that many seconds the process dumps a post-mortem and exits."""
+    rank = os.environ.get("RANK", "0")
     if rank == "0" or os.environ.get("DTG_BENCH_VERBOSE"):
         print(f"[bench rank {rank} +{time.time() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
-    try:
-        faulthandler.cancel_dump_traceback_later()
-        if budget_s:
-            faulthandler.dump_traceback_later(budget_s, exit=True, file=sys.__stderr__)
-    except Exception:  # stderr without a file descriptor (captured): run without the watchdog
-        pass
+    _WATCH["stage"] = msg
+    _WATCH["deadline"] = (time.time() + budget_s) if budget_s else None
+    if budget_s and _WATCH["thread"] is None and not os.environ.get("DTG_BENCH_NO_WATCHDOG"):
+        _WATCH["thread"] = threading.Thread(target=_watch_loop, daemon=True, name="bench-watchdog")
+        _WATCH["thread"].start()
 
 
 def run_b200(args):
-    _stage("importing torch", budget_s=1800)
+    _stage("importing torch", budget_s=BUDGET["import"])
+    os.environ.setdefault("DTG_DIST_TIMEOUT_S", "150")       # a wedged collective aborts with a stack, well inside
+    os.environ.setdefault("TORCH_NCCL_DUMP_ON_TIMEOUT", "1")  # the driver's per-N limit
     import torch
 
     from distributed_training_guide_b200 import _ext
@@ -149,7 +183,7 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun for N>1"
     par = args.parallelism if world > 1 else "single"
-    _stage(f"building the {par} engine on {world} GPU(s) (process group, NVLink symmetric memory, model)", budget_s=1800)
+    _stage(f"building the {par} engine on {world} GPU(s) (process group, NVLink symmetric memory, model)", budget_s=BUDGET["build"])
     eng = TrainEngine.create(args.model, parallelism=par, batch_size=args.batch, seq_length=args.seq_len,
                              tensor_parallel=args.tensor_parallel, num_layers=args.layers)
     dev = eng.device
@@ -166,7 +200,7 @@ def run_b200(args):
     ddp_engine = getattr(eng.model, "engine", None)
     if world > 1 and hasattr(ddp_engine, "measure_tail"):
         ddp_engine.measure_tail = True   # two CUDA events per step: exposed communication = comm stream past backward
-    _stage(f"engine ready; {args.warmup} warm-up steps", budget_s=900)
+    _stage(f"engine ready; {args.warmup} warm-up steps", budget_s=BUDGET["warmup"] + 2 * args.warmup)
     for i in range(args.warmup):
         eng.step(dev_batches[i])
     torch.cuda.synchronize(dev)
@@ -192,7 +226,7 @@ def run_b200(args):
     elif os.environ.get("DTG_CPU_PROFILE"):
         eng.step(dev_batches[args.warmup])
     # ---- region 1: device-timed steps, batch resident on the GPU --------------------------------
-    _stage(f"timing {args.steps} steps (device events)", budget_s=900)
+    _stage(f"timing {args.steps} steps (device events)", budget_s=BUDGET["timed"] + 2 * args.steps)
     _barrier_sync(dev)
     l0 = _ext.launch_count()
     with ClockSampler(dev.index or 0) as clocks:
@@ -205,7 +239,7 @@ def run_b200(args):
     launches = _ext.launch_count() - l0
     ms_dev = _dist_max(s.elapsed_time(e), dev) / args.steps
     # ---- region 2: end to end through the public API: pinned H2D every step + loss D2H every step ---
-    _stage(f"timing {args.steps} steps end to end (pinned H2D + loss D2H every step)", budget_s=900)
+    _stage(f"timing {args.steps} steps end to end (pinned H2D + loss D2H every step)", budget_s=BUDGET["e2e"] + 2 * args.steps)
     eng.step(host_batches[args.steps])
     _barrier_sync(dev)
     s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -250,7 +284,7 @@ def run_b200(args):
     }
     if rank == 0:
         print(json.dumps(out), flush=True)
-    _stage("done; tearing down", budget_s=300)
+    _stage("done; tearing down", budget_s=BUDGET["teardown"])
     eng.close()
     from distributed_training_guide_b200.parallel.bootstrap import shutdown
 

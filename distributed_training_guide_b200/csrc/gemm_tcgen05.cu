@@ -106,9 +106,10 @@ gemm_bf16_kernel(const __grid_constant__ TmapSet<(A_MODE ? kMaxRanks : 1)> tmAs,
       for (int p = 0; p < t_; ++p) st_release_sys(dist.pads[p] + cidx * kMaxRanks + rk, dist.bar_epoch);
       for (int p = 0; p < t_; ++p) {
         const uint32_t* mine = dist.pads[rk] + cidx * kMaxRanks + p;
-        const long long t0 = clock64();
+        const unsigned long long t0 = global_timer_ns();
         while ((int32_t)(ld_acquire_sys(mine) - dist.bar_epoch) < 0)
-          if (clock64() - t0 > 20000000000LL) break;
+          if (global_timer_ns() - t0 > kWaitTimeoutNs)  // a peer never launched the matching GEMM: fail loudly
+            wait_timeout_trap("all-gather GEMM: peer did not arrive at the entry barrier", __FILE__, __LINE__);
       }
       constexpr uint32_t PIECE = Cfg::STAGE_BYTES;   // one ring slot = one pipeline stage of the GEMM smem
       constexpr int NB = Cfg::STAGES, AHEAD = NB - 2;
@@ -158,9 +159,11 @@ gemm_bf16_kernel(const __grid_constant__ TmapSet<(A_MODE ? kMaxRanks : 1)> tmAs,
         int a_m0 = m0;
         if constexpr (A_MODE == 3) {  // fetched tile: wait until the communication CTAs published it
           if (tm_ / (local_m_tiles > 0 ? local_m_tiles : 1) != dist.rank) {
-            const long long t0 = clock64();
+            const unsigned long long t0 = global_timer_ns();
             while ((int32_t)(ld_acquire_gpu(dist.ag_flags + tm_) - dist.ag_epoch) < 0)
-              if (clock64() - t0 > 20000000000LL) break;
+              if (global_timer_ns() - t0 > kWaitTimeoutNs)  // never read an unfetched tile
+                wait_timeout_trap("all-gather GEMM: row tile was never published by the communication CTAs",
+                                  __FILE__, __LINE__);
             fence_proxy_async_all();
           }
         }

@@ -7,6 +7,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cstdint>
+#include <cstdio>
 
 namespace dtg {
 namespace ptx {
@@ -82,10 +83,35 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// A wait that can never complete (lost arrive, wrong tx byte count, dead peer) must not wedge the GPU and the seven
+// ranks behind it: after ~8 s of polling the thread reports itself like a device assert does (file:line, block,
+// thread) and traps, so the launch fails loudly and the host raises.  The slow path costs one compare per 64 Ki
+// failed polls; the fast path is the bare try_wait.
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr unsigned long long kWaitTimeoutNs = 8ULL * 1000 * 1000 * 1000;
+static __device__ __noinline__ void wait_timeout_trap(const char* what, const char* file, unsigned line) {
+  printf("[dtg] %s:%u: %s — block (%d,%d,%d) thread %d; trapping\n", file, line, what, (int)blockIdx.x, (int)blockIdx.y,
+         (int)blockIdx.z, (int)threadIdx.x);
+  __threadfence_system();
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait_at(uint64_t* bar, uint32_t parity, const char* file, unsigned line) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t polls = 0;
+  unsigned long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if ((++polls & 0xFFFFu) == 0) {
+      const unsigned long long now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kWaitTimeoutNs) wait_timeout_trap("mbarrier wait timed out (pipeline deadlock)", file, line);
+    }
   }
 }
+#define mbar_wait(bar, parity) ::dtg::ptx::mbar_wait_at((bar), (parity), __FILE__, __LINE__)
 
 // sub-CTA barrier over `nthreads` threads (ids 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {

@@ -54,7 +54,11 @@ def detect_rank_world():
 
 
 def init_distributed(device_type: Optional[str] = None, local_rank: Optional[int] = None,
-                     timeout_s: int = 1800, force: bool = False) -> DistEnv:
+                     timeout_s: Optional[int] = None, force: bool = False) -> DistEnv:
+    # collective timeout: long enough for a rank-0-first model download, short enough that a wedged job dies with
+    # a stack instead of burning an allocation (DTG_DIST_TIMEOUT_S overrides; bench.py sets 150 s)
+    if timeout_s is None:
+        timeout_s = int(os.environ.get("DTG_DIST_TIMEOUT_S", "600"))
     rank, world, env_local = detect_rank_world()
     if device_type is None:
         device_type = "cuda" if torch.cuda.is_available() else "cpu"

@@ -28,6 +28,18 @@ def allocated_bytes() -> int:
     return int(c.symm_allocated_bytes()) if c is not None and hasattr(c, "symm_allocated_bytes") else 0
 
 
+def post_mortem(timeout_s: float = 5.0):
+    """Signal-pad state of every live group, read on a side stream with a bounded wait so it also works while a
+    kernel of this process is spinning on the device (a hung run's last words; used by bench.py's watchdog)."""
+    lines = []
+    for i, g in enumerate(list(_LIVE_GROUPS)):
+        try:
+            lines.append(f"symm group {i} (rank {g.rank}/{g.world}): " + g.describe_pads(timeout_s=timeout_s))
+        except Exception as e:  # pragma: no cover - diagnostics only
+            lines.append(f"symm group {i}: unavailable ({e!r})")
+    return lines
+
+
 class SymmBuffer:
     """One symmetric allocation: ``local`` (this rank's memory as a tensor) + every rank's base pointer
     (+ the NVSwitch multicast address of the allocation when it was bound to one, else 0)."""
@@ -178,17 +190,33 @@ class SymmGroup:
             raise RuntimeError(f"NVLink barrier timed out waiting for rank {v - 1} (group rank {self.rank}); "
                                + self.describe_pads())
 
-    def describe_pads(self) -> str:
+    def describe_pads(self, timeout_s: float = 5.0) -> str:
         """Signal-pad state for a post-mortem: per peer, the range of epochs this rank has received over its
         channels, next to the epoch this rank's host has issued.  A peer stuck at a lower epoch never launched
-        (or never finished) the matching collective."""
+        (or never finished) the matching collective.  The read runs on its own stream and gives up after
+        ``timeout_s`` so it cannot itself hang behind a spinning kernel."""
+        import time
+
         try:
             ch = int(self.C.SYMM_MAX_CHANNELS)
             mr = int(self.C.SYMM_PAD_BYTES) // 4 // ch           # uint32 [channels][max ranks]
             words = self.pads.local[: ch * mr * 4].view(torch.int32)
-            tab = words.view(ch, mr)[: self.comm_blocks, : self.world].cpu()
+            host = torch.empty(ch * mr + 1, dtype=torch.int32, pin_memory=True)
+            side = torch.cuda.Stream(device=self.device)
+            done = torch.cuda.Event()
+            with torch.cuda.stream(side):
+                host[: ch * mr].copy_(words, non_blocking=True)
+                host[ch * mr:].copy_(self.err, non_blocking=True)
+                done.record(side)
+            t0 = time.time()
+            while not done.query():
+                if time.time() - t0 > timeout_s:
+                    return f"(pad read did not complete within {timeout_s:.0f} s; issued locally: {self.epoch})"
+                time.sleep(0.01)
+            tab = host[: ch * mr].view(ch, mr)[: self.comm_blocks, : self.world]
             seen = ", ".join(f"rank {p}: {int(tab[:, p].min())}..{int(tab[:, p].max())}" for p in range(self.world))
-            return f"epochs received per peer (min..max over {self.comm_blocks} channels): {seen}; issued locally: {self.epoch}"
+            return (f"epochs received per peer (min..max over {self.comm_blocks} channels): {seen}; "
+                    f"issued locally: {self.epoch}; error flag: {int(host[ch * mr])}")
         except Exception as e:  # pragma: no cover - best effort diagnostics
             return f"(pad state unavailable: {e})"
 

@@ -523,6 +523,21 @@ class FSDPEngine:
         for s in self.shards:
             self.optimizer.state[s.param]["step"] = int(steps.get(s.name, 0))
 
+    def after_load(self):
+        """A checkpoint was loaded into the GPU shards: refresh what was derived from them at construction — with
+        ``--cpu-offload`` the host master copy AdamW updates (it was snapshotted from the freshly initialised
+        weights in ``build_optimizer`` and would otherwise overwrite the loaded ones at the first step)."""
+        if self.optimizer is None:
+            return
+        for s in self.shards:
+            st = self.optimizer.state[s.param]
+            if "cpu_param" in st:
+                st["cpu_param"].copy_(s.param)
+        # every full slot is stale now
+        for i in range(len(self.slot_owner)):
+            self.slot_owner[i] = None
+        self._unsharded.clear()
+
     def full_state_dict(self):
         """Gather every group and return an HF-named full state dict (for export / tests)."""
         out = {}

@@ -294,23 +294,18 @@ class FullyShardedDataParallel(Strategy):
         ws = env.world_size if env.distributed else 1
         if env.device.type == "cuda":
             torch.cuda.synchronize()
-        ckpt_utils.save_sharded(exp_dir, self.engine.sharded_state(), lr_scheduler, state, env.rank, ws)
-        if env.rank == 0:
-            import json
-
-            with open(Path(exp_dir) / "optimizer_steps.json", "w") as fp:
-                json.dump(self.engine.optimizer_steps(), fp)
+        ckpt_utils.save_sharded(exp_dir, self.engine.sharded_state(), lr_scheduler, state, env.rank, ws,
+                                extra_rank0={"optimizer_steps.json": self.engine.optimizer_steps()})
         self.barrier()
 
     def load_checkpoint(self, exp_dir, model, optimizer, lr_scheduler):
-        import json
-
         env = self.env
         ws = env.world_size if env.distributed else 1
         st = ckpt_utils.load_sharded(exp_dir, self.engine.sharded_state(), lr_scheduler, env.device, env.rank, ws)
-        steps_file = Path(exp_dir) / "optimizer_steps.json"
-        if steps_file.exists():
-            self.engine.set_optimizer_steps(json.loads(steps_file.read_text()))
+        steps = ckpt_utils.load_json_side_file(exp_dir, "optimizer_steps.json")
+        if steps is not None:
+            self.engine.set_optimizer_steps(steps)
+        self.engine.after_load()
         return st
 
     def make_experiment_dir(self, exp_dir: Path):
@@ -484,13 +479,29 @@ class TwoDParallel(Strategy):
         ws = env.world_size if env.distributed else 1
         if env.device.type == "cuda":
             torch.cuda.synchronize()
-        ckpt_utils.save_sharded(exp_dir, self._sharded_state(optimizer), lr_scheduler, state, env.rank, ws)
+        ckpt_utils.save_sharded(exp_dir, self._sharded_state(optimizer), lr_scheduler, state, env.rank, ws,
+                                extra_rank0={"optimizer_steps.json": self._optimizer_steps(optimizer)})
         self.barrier()
 
     def load_checkpoint(self, exp_dir, model, optimizer, lr_scheduler):
         env = self.env
         ws = env.world_size if env.distributed else 1
-        return ckpt_utils.load_sharded(exp_dir, self._sharded_state(optimizer), lr_scheduler, env.device, env.rank, ws)
+        st = ckpt_utils.load_sharded(exp_dir, self._sharded_state(optimizer), lr_scheduler, env.device, env.rank, ws)
+        steps = ckpt_utils.load_json_side_file(exp_dir, "optimizer_steps.json")
+        if steps is not None:  # AdamW bias correction continues where it stopped (moments alone are not enough)
+            if self.engine is not None:
+                self.engine.set_optimizer_steps(steps)
+            else:
+                for g in self.groups:
+                    optimizer.state[g.param]["step"] = int(steps.get(g.name, 0))
+        if self.engine is not None:
+            self.engine.after_load()
+        return st
+
+    def _optimizer_steps(self, optimizer):
+        if self.engine is not None:
+            return self.engine.optimizer_steps()
+        return {g.name: int(optimizer.state[g.param]["step"]) for g in self.groups}
 
     def _sharded_state(self, optimizer):
         if self.engine is not None:

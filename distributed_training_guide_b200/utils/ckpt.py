@@ -78,13 +78,25 @@ def set_rng_state(st):
         torch.cuda.set_rng_state_all(st["cuda"])
 
 
+def _restore_lr(lr_scheduler):
+    """``LRScheduler.load_state_dict`` restores the schedule position but not the optimizer's current ``lr`` (torch
+    relies on ``optimizer.load_state_dict`` for that); our flat optimizers persist only moments and step counters,
+    so put the scheduled value back — otherwise the first resumed step runs at the initial learning rate."""
+    opt = getattr(lr_scheduler, "optimizer", None)
+    last = getattr(lr_scheduler, "_last_lr", None)
+    if opt is not None and last is not None:
+        for g, lr in zip(opt.param_groups, last):
+            g["lr"] = lr
+
+
 # -- full (unsharded) checkpoints: chapters 01 / 02 -------------------------------------------
 def save_full(exp_dir: Path, model, optimizer, lr_scheduler, state, rank=0, world_size=1,
               save_optimizer=True, deterministic=False):
     """Rank 0 writes model/lr_scheduler/state; every rank writes its optimizer shard."""
     exp_dir = Path(exp_dir)
-    if rank == 0:
-        exp_dir.mkdir(parents=True, exist_ok=True)
+    # every rank: on node-local disks the other nodes' ranks write their optimizer shard into their own copy of the
+    # directory (reference chapters 02/03 cover that layout); exist_ok makes the shared-mount case a no-op
+    exp_dir.mkdir(parents=True, exist_ok=True)
     if world_size > 1:
         dist.barrier()
     if save_optimizer and optimizer is not None:
@@ -117,7 +129,13 @@ def load_full(exp_dir: Path, model, optimizer, lr_scheduler, device, rank=0, wor
     opt_path = exp_dir / ("optimizer.pt" if world_size == 1 else f"optimizer.rank{rank}.pt")
     if optimizer is not None and opt_path.exists():
         optimizer.load_state_dict(_load(opt_path))
+    elif optimizer is not None:
+        import logging
+
+        logging.getLogger("dtg_b200").warning(
+            "%s not found (different world size or node-local disk?): optimizer state starts from zero", opt_path)
     lr_scheduler.load_state_dict(_load(exp_dir / "lr_scheduler.pt"))
+    _restore_lr(lr_scheduler)
     rng_path = exp_dir / ("rng.pt" if world_size == 1 else f"rng.rank{rank}.pt")
     if deterministic and rng_path.exists():
         set_rng_state(torch.load(rng_path, weights_only=False))
@@ -138,9 +156,19 @@ def save_sharded(exp_dir: Path, shards: dict, lr_scheduler, state, rank, world_s
     dcp.save(sd, checkpoint_id=str(exp_dir / "checkpoint"))
     if rank == 0:
         _atomic_save(lr_scheduler.state_dict(), exp_dir / "lr_scheduler.pt")
+        for name, obj in (extra_rank0 or {}).items():  # small JSON side files (e.g. AdamW step counters): written
+            tmp = exp_dir / (name + ".tmp")             # atomically and BEFORE state.json, the completeness marker
+            with open(tmp, "w") as fp:
+                json.dump(obj, fp)
+            os.replace(tmp, exp_dir / name)
         save_state_json(exp_dir, state)
     if world_size > 1:
         dist.barrier()
+
+
+def load_json_side_file(exp_dir: Path, name: str):
+    p = Path(exp_dir) / name
+    return json.loads(p.read_text()) if p.exists() else None
 
 
 def load_sharded(exp_dir: Path, shards: dict, lr_scheduler, device, rank, world_size):
@@ -157,6 +185,7 @@ def load_sharded(exp_dir: Path, shards: dict, lr_scheduler, device, rank, world_
             if local.data_ptr() != v.data_ptr():
                 v.copy_(local)
     lr_scheduler.load_state_dict(torch.load(exp_dir / "lr_scheduler.pt", map_location=device, weights_only=True))
+    _restore_lr(lr_scheduler)
     return load_state_json(exp_dir)
 
 

@@ -4,6 +4,8 @@
 // cuts it into [batch, seq] int64 batches (shuffled per epoch, partitioned over data-parallel ranks like
 // DistributedSampler with drop_last) and writes them into a ring of PINNED host buffers, so the training
 // loop's `next()` is a queue pop and the H2D copy is a true async DMA.
+#include <ATen/cuda/CUDAContext.h>
+#include <cuda_runtime.h>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -46,11 +48,15 @@ class TokenLoader {
       auto t = torch::empty({batch_, seq_}, opts);
       ring_.push_back(pin ? t.pin_memory() : t);
     }
+    copied_.assign((size_t)depth_, nullptr);
+    guard_.assign((size_t)depth_, 0);
     set_epoch(0);
   }
 
   ~TokenLoader() {
     stop();
+    for (auto e : copied_)
+      if (e) cudaEventDestroy(e);
     if (base_ && base_ != MAP_FAILED) munmap((void*)base_, bytes_);
     if (fd_ >= 0) ::close(fd_);
   }
@@ -71,16 +77,36 @@ class TokenLoader {
     worker_ = std::thread([this] { this->run(); });
   }
 
-  // next batch: a view of a pinned ring slot, valid until `depth - 1` further calls
+  // next batch: a view of a pinned ring slot.  The slot becomes refillable `depth - 1` calls later AND, if the
+  // consumer reported an asynchronous copy out of it (`mark_copied`), only once that copy has executed.
   torch::Tensor next() {
     std::unique_lock<std::mutex> lk(mu_);
     TORCH_CHECK(consumed_ < n_batches_, "epoch exhausted: call set_epoch()");
     cv_.wait(lk, [this] { return produced_ > consumed_; });
-    torch::Tensor out = ring_[consumed_ % depth_];
+    last_slot_ = consumed_ % depth_;
+    torch::Tensor out = ring_[last_slot_];
     ++consumed_;
-    // the slot handed out `depth-1` calls ago may now be refilled
     cv_.notify_all();
     return out;
+  }
+
+  // The consumer enqueued `non_blocking` H2D copies out of the slot handed out by the last next() on the CURRENT
+  // CUDA stream: record an event behind them; the producer waits on it before overwriting the slot.  (A call
+  // count alone is not enough: the host may run many steps ahead of the device, so the DMA that reads the slot
+  // may not have executed when the ring wraps — torch's pinned caching allocator guards this with stream events
+  // too.)
+  void mark_copied() {
+    int64_t slot;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      slot = last_slot_;
+    }
+    if (slot < 0) return;
+    cudaEvent_t& e = copied_[(size_t)slot];
+    if (!e) C10_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    C10_CUDA_CHECK(cudaEventRecord(e, at::cuda::getCurrentCUDAStream().stream()));
+    std::lock_guard<std::mutex> lk(mu_);
+    guard_[(size_t)slot] = 1;
   }
 
  private:
@@ -100,6 +126,17 @@ class TokenLoader {
         // keep one slot of slack: the consumer may still be copying the slot it was handed last
         cv_.wait(lk, [this] { return done_ || produced_ - consumed_ < depth_ - 1; });
         if (done_) return;
+      }
+      {
+        cudaEvent_t e = nullptr;
+        {
+          std::lock_guard<std::mutex> lk(mu_);
+          if (guard_[(size_t)(b % depth_)]) {
+            e = copied_[(size_t)(b % depth_)];
+            guard_[(size_t)(b % depth_)] = 0;
+          }
+        }
+        if (e) cudaEventSynchronize(e);  // the DMA out of this slot has executed
       }
       int64_t* dst = ring_[b % depth_].data_ptr<int64_t>();
       for (int64_t i = 0; i < batch_; ++i) {
@@ -129,6 +166,9 @@ class TokenLoader {
   int64_t n_chunks_ = 0, per_rank_ = 0, n_batches_ = 0;
   std::vector<int64_t> order_;
   std::vector<torch::Tensor> ring_;
+  std::vector<cudaEvent_t> copied_;  // per slot: recorded behind the consumer's async copies out of it
+  std::vector<char> guard_;          // per slot: copied_[slot] must be waited for before the next refill
+  int64_t last_slot_ = -1;
   std::thread worker_;
   std::mutex mu_;
   std::condition_variable cv_;
@@ -147,6 +187,7 @@ void bind_dataloader(pybind11::module_& m) {
       .def("num_batches", &TokenLoader::num_batches)
       .def("num_chunks", &TokenLoader::num_chunks)
       .def("set_epoch", &TokenLoader::set_epoch, pybind11::call_guard<pybind11::gil_scoped_release>())
-      .def("next", &TokenLoader::next, pybind11::call_guard<pybind11::gil_scoped_release>());
+      .def("next", &TokenLoader::next, pybind11::call_guard<pybind11::gil_scoped_release>())
+      .def("mark_copied", &TokenLoader::mark_copied);
 }
 }  // namespace dtg

@@ -85,7 +85,10 @@ class TrainEngine:
         s = self.strategy
         dev = self.device
         ev = self._phase_events() if self.phase_timing else None
+        src = batch
         batch = {k: (v.to(dev, non_blocking=True) if v.device != dev else v) for k, v in batch.items()}
+        if hasattr(src, "copied") and dev.type == "cuda":
+            src.copied()  # native loader ring slot: guard it until these async copies have executed
         s.pre_step(self.model)
         batch = s.prepare_batch(batch)
         if ev:

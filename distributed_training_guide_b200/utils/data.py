@@ -189,7 +189,20 @@ class NativeTokenLoader:
         self._started = False
         for _ in range(len(self)):
             ids = self._loader.next()
-            yield {"input_ids": ids, "attention_mask": torch.ones_like(ids), "labels": ids}
+            yield RingBatch({"input_ids": ids, "attention_mask": torch.ones_like(ids), "labels": ids}, self._loader)
+
+
+class RingBatch(dict):
+    """A batch whose tensors alias a pinned ring slot of the native loader.  ``to_device`` reports its asynchronous
+    H2D copies back (``copied()``) so the producer thread never overwrites a slot whose DMA has not executed yet."""
+
+    def __init__(self, tensors, loader):
+        super().__init__(tensors)
+        self._loader = loader
+
+    def copied(self):
+        if torch.cuda.is_available():
+            self._loader.mark_copied()
 
 
 def collate(samples):
@@ -232,4 +245,7 @@ def build_dataloader(dataset, batch_size, dp_size=1, dp_rank=0, seed=0, distribu
 
 def to_device(batch, device):
     nb = torch.device(device).type == "cuda"
-    return {k: v.to(device=device, non_blocking=nb) for k, v in batch.items()}
+    out = {k: v.to(device=device, non_blocking=nb) for k, v in batch.items()}
+    if nb and isinstance(batch, RingBatch):
+        batch.copied()
+    return out

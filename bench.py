@@ -150,12 +150,52 @@ def _post_mortem(stage):
     os._exit(3)
 
 
+_PROGRESS = {"ticks": 0, "t": None, "engine": None, "reported": False}
+
+
+def _tick():
+    _PROGRESS["ticks"] += 1
+    _PROGRESS["t"] = time.time()
+
+
+def _stall_report(idle_s):
+    """A step loop has not moved for a while although its stage budget is not used up yet: say where the host is
+    (stacks) and how far the device got (event queries only — nothing here can block behind a wedged kernel)."""
+    import faulthandler
+
+    rank = os.environ.get("RANK", "0")
+    w = sys.__stderr__
+    w.write(f"[bench rank {rank}] STALL: no step completed for {idle_s:.0f} s in stage '{_WATCH['stage']}' "
+            f"(after {_PROGRESS['ticks']} steps)\n")
+    try:
+        import torch
+
+        eng = _PROGRESS["engine"]
+        w.write(f"[bench rank {rank}] compute stream idle: {torch.cuda.current_stream(eng.device).query()}\n")
+        e = getattr(eng.model, "engine", None)
+        if e is not None and hasattr(e, "describe_progress"):
+            w.write(f"[bench rank {rank}] {e.describe_progress()}\n")
+        symm = sys.modules.get("distributed_training_guide_b200.parallel.symm")
+        for line in (symm.post_mortem(timeout_s=3.0) if symm is not None else []):
+            w.write(f"[bench rank {rank}] {line}\n")
+    except Exception as e:  # pragma: no cover - diagnostics only
+        w.write(f"[bench rank {rank}] (device state unavailable: {e!r})\n")
+    w.flush()
+    faulthandler.dump_traceback(file=w, all_threads=True)
+    w.flush()
+
+
 def _watch_loop():
+    stall_s = float(os.environ.get("DTG_BENCH_STALL_S", "0") or 0)
     while True:
         time.sleep(0.5)
         d = _WATCH["deadline"]
         if d is not None and time.time() > d:
             _post_mortem(_WATCH["stage"])
+        t = _PROGRESS["t"]
+        if stall_s and t is not None and not _PROGRESS["reported"] and time.time() - t > stall_s:
+            _PROGRESS["reported"] = True
+            _stall_report(time.time() - t)
 
 
 def _stage(msg, budget_s=None):
@@ -173,6 +213,13 @@ def _stage(msg, budget_s=None):
 
 def run_b200(args):
     _stage("importing torch", budget_s=BUDGET["import"])
+    try:  # a rank killed from outside (torchrun tearing the job down after a peer failed) still says where it was
+        import faulthandler
+        import signal
+
+        faulthandler.register(signal.SIGTERM, file=sys.__stderr__, all_threads=True, chain=True)
+    except Exception:
+        pass
     os.environ.setdefault("DTG_DIST_TIMEOUT_S", "150")       # a wedged collective aborts with a stack, well inside
     os.environ.setdefault("TORCH_NCCL_DUMP_ON_TIMEOUT", "1")  # the driver's per-N limit
     import torch
@@ -201,9 +248,15 @@ def run_b200(args):
     if world > 1 and hasattr(ddp_engine, "measure_tail"):
         ddp_engine.measure_tail = True   # two CUDA events per step: exposed communication = comm stream past backward
     _stage(f"engine ready; {args.warmup} warm-up steps", budget_s=BUDGET["warmup"] + 2 * args.warmup)
+    _PROGRESS["engine"] = eng
+    _tick()
     for i in range(args.warmup):
         eng.step(dev_batches[i])
+        if os.environ.get("DTG_BENCH_SYNC_WARMUP"):  # debug: one step at a time, so a stall report names the step
+            torch.cuda.synchronize(dev)
+        _tick()
     torch.cuda.synchronize(dev)
+    _PROGRESS["t"] = None
     eng.strategy.check_health()
     if os.environ.get("DTG_CPU_PROFILE") and rank == 0:  # host-side cost of one step (diagnostics)
         import cProfile

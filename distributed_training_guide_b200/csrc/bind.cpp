@@ -183,4 +183,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   dtg::bind_attention(m);
   dtg::bind_tp(m);
   dtg::bind_dataloader(m);
+  dtg::bind_symm_vmm(m);
 }

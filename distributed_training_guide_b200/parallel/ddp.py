@@ -86,6 +86,9 @@ class DataParallelEngine:
         self.measure_tail, self._tails = False, []  # bench.py: two events per step -> exposed_comm_ms()
         # DTG_COMM_TRACE=1: CUDA events around every bucket kernel (see comm_trace_summary)
         self.trace = [] if (self.use_kernels and os.environ.get("DTG_COMM_TRACE")) else None
+        # DTG_DEBUG_MARKERS=1: keep, per bucket of the current step, the event recorded on the compute stream when
+        # the bucket became ready and the one behind its kernel on the communication stream (stall post-mortems)
+        self.markers = {} if (self.use_kernels and os.environ.get("DTG_DEBUG_MARKERS")) else None
 
     # -- hooks called by the model ---------------------------------------------------------------
     def pre_forward(self, model):
@@ -163,6 +166,22 @@ class DataParallelEngine:
                 self.trace.append((g.name, t0, t1))
                 return
             self._run_bucket(g, gbuf)
+            if self.markers is not None:
+                done = torch.cuda.Event()
+                done.record(self.comm_stream)
+                self.markers[g.name] = (ev, done)
+
+    def describe_progress(self) -> str:
+        """Which buckets of the step in flight have (a) become ready on the compute stream and (b) finished their
+        fused kernel on the communication stream — event queries only, safe to call while the device is wedged."""
+        if not self.markers:
+            return "(no markers: set DTG_DEBUG_MARKERS=1)"
+        ready = [n for n, (a, b) in self.markers.items() if a.query()]
+        done = [n for n, (a, b) in self.markers.items() if b.query()]
+        names = list(self.markers)
+        return (f"buckets launched this step: {len(names)} (last {names[-1]}); compute stream reached: "
+                f"{ready[-1] if ready else None} ({len(ready)}); comm stream finished: {done[-1] if done else None} "
+                f"({len(done)}); comm stream idle: {self.comm_stream.query()}")
 
     def exposed_comm_ms(self, last_steps=None):
         """Mean time per step the communication stream kept running after backward had finished on the compute

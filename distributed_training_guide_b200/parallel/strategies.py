@@ -176,6 +176,11 @@ def _flat_groups_on(strategy, model, world_size=1, pg=None):
     if device.type == "cuda":
         sg = symm_mod.SymmGroup(device, pg=pg) if (world_size > 1 or pg is not None) else symm_mod.SymmGroup(device, ranks=[0])
         registry = {}
+        # parameters + gradients of every group come out of ONE symmetric chunk (one handle exchange)
+        esize = torch.empty((), dtype=strategy.dtype()).element_size()
+        n_groups = len(list(model.model.layers)) + 2 if hasattr(model, "model") else 64
+        sg.reserve(2 * esize * sum(p.numel() for p in model.parameters())
+                   + 2 * n_groups * (8 * world_size * 16 * esize + 2 * sg.ALIGN))
         groups = build_groups(model, device, strategy.dtype(), world_size=world_size, alloc=sg.allocator(registry))
         return groups, sg, registry
     return build_groups(model, device, strategy.dtype(), world_size=world_size), None, {}

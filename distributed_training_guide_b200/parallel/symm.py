@@ -25,7 +25,8 @@ _LIVE_GROUPS = []
 
 def allocated_bytes() -> int:
     c = _ext.load(False)
-    return int(c.symm_allocated_bytes()) if c is not None and hasattr(c, "symm_allocated_bytes") else 0
+    n = int(c.symm_allocated_bytes()) if c is not None and hasattr(c, "symm_allocated_bytes") else 0  # cudaMalloc'ed
+    return n + sum(ch.size for g in _LIVE_GROUPS for ch in g._chunks if isinstance(ch, _VmmChunk))
 
 
 def post_mortem(timeout_s: float = 5.0):
@@ -57,7 +58,141 @@ class SymmBuffer:
         return off // view.element_size()
 
 
+class _StoreComm:
+    """CPU-side rendezvous of one process group over the c10d store (TCPStore): all-gather of small objects and a
+    barrier.  Symmetric-memory set-up uses ONLY this — no NCCL kernel runs while buffers are being created and
+    mapped (round 1 issued ~140 NCCL collectives there, next to cudaMalloc / IPC opens)."""
+
+    _SEQ = {}
+
+    def __init__(self, pg):
+        import torch.distributed.distributed_c10d as c10d
+
+        self.store = c10d._get_default_store()
+        ranks = tuple(dist.get_process_group_ranks(pg if pg is not None else dist.group.WORLD))
+        self.rank = dist.get_rank(pg)
+        self.world = len(ranks)
+        n = _StoreComm._SEQ.get(ranks, 0)          # construction is collective: same order on every member
+        _StoreComm._SEQ[ranks] = n + 1
+        self.prefix = "dtg/symm/" + "-".join(map(str, ranks)) + f"/{n}"
+        self.seq = 0
+
+    def all_gather(self, obj):
+        import pickle
+
+        k = f"{self.prefix}/ag{self.seq}"
+        self.seq += 1
+        self.store.set(f"{k}/{self.rank}", pickle.dumps(obj))
+        return [pickle.loads(self.store.get(f"{k}/{r}")) for r in range(self.world)]
+
+    def barrier(self):
+        self.all_gather(None)
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class _IpcChunk:
+    """One cudaMalloc + (several ranks) one CUDA-IPC handle exchange: the single-rank case and the fallback when
+    the system cannot export VMM allocations as file descriptors."""
+
+    def __init__(self, group, nbytes):
+        C = group.C
+        self.raw, handle = C.symm_alloc(int(nbytes), group.device.index or 0)
+        self.size = self.raw.numel()
+        self.bases, self._opened = [], []
+        handles = group.comm.all_gather(bytes(handle)) if group.world > 1 else [None]
+        for r, h in enumerate(handles):
+            if r == group.rank:
+                self.bases.append(self.raw.data_ptr())
+            else:
+                p = C.symm_open(h, group.device.index or 0)
+                self._opened.append(p)
+                self.bases.append(p)
+        self.mc_base = 0
+        if group.world > 1:
+            group.comm.barrier()
+        self._C = C
+
+    def local_view(self, off, n):
+        return self.raw[off:off + n]
+
+    def close(self):
+        for p in self._opened:
+            try:
+                self._C.symm_close(p)
+            except Exception:
+                pass
+        self._opened = []
+
+
+class _VmmChunk:
+    """One VMM chunk (``csrc/symm_vmm.cpp``): my physical allocation + every peer's, mapped side by side, and the
+    NVLS multicast view.  File descriptors travel over an abstract Unix socket (SCM_RIGHTS); ordering over the store."""
+
+    def __init__(self, group, nbytes):
+        import socket
+        import struct
+
+        C, comm, world, rank = group.C, group.comm, group.world, group.rank
+        self.chunk = C.VmmChunk(group.device.index or 0, int(nbytes), world, rank, group.multicast)
+        self.size = int(self.chunk.size())
+        my_fd = int(self.chunk.export_fd())
+        mc_fd = int(self.chunk.mc_create_export()) if (group.multicast and rank == 0) else -1
+        tag = f"{group.token}-{group._n_chunks}"
+        addr = lambda r: f"\0dtg-symm-{tag}-{r}"  # noqa: E731  (abstract namespace: nothing to unlink)
+        lst = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        try:
+            lst.bind(addr(rank))
+            lst.listen(2 * world)
+            comm.barrier()                                   # every listener exists
+            for peer in range(world):
+                if peer == rank:
+                    continue
+                with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as c:
+                    c.connect(addr(peer))
+                    fds = [my_fd] + ([mc_fd] if mc_fd >= 0 else [])
+                    socket.send_fds(c, [struct.pack("ii", rank, len(fds))], fds)
+            for _ in range(world - 1):
+                conn, _ = lst.accept()
+                with conn:
+                    msg, fds, _, _ = socket.recv_fds(conn, 8, 2)
+                    peer, nfd = struct.unpack("ii", msg)
+                    assert len(fds) == nfd, "file descriptors were lost in transit"
+                    self.chunk.import_peer(peer, fds[0])
+                    if nfd == 2:
+                        self.chunk.mc_import(fds[1])
+                    for fd in fds:
+                        os.close(fd)
+        finally:
+            lst.close()
+        os.close(my_fd)
+        if mc_fd >= 0:
+            os.close(mc_fd)
+        self.chunk.map_all()
+        self.mc_base = 0
+        if group.multicast:
+            self.chunk.mc_add_device()
+            comm.barrier()                                   # every device joined the multicast team
+            self.chunk.mc_bind_and_map()
+            self.mc_base = int(self.chunk.mc_base())
+        comm.barrier()                                       # every rank's memory is zeroed, mapped and bound
+        base = int(self.chunk.base())
+        self.bases = [base + r * self.size for r in range(world)]
+
+    def local_view(self, off, n):
+        return self.chunk.local_view(int(off), int(n))
+
+    def close(self):
+        self.chunk.release()
+
+
 class SymmGroup:
+    ALIGN = 4096                  # sub-allocation alignment inside a chunk (TMA / vector / shard alignment)
+    FIRST_CHUNK = 64 << 20
+    MAX_GROWTH = 4 << 30
+
     def __init__(self, device: torch.device, pg=None, ranks: Optional[List[int]] = None,
                  comm_blocks: Optional[int] = None):
         self.C = _ext.load(required=True)
@@ -77,53 +212,57 @@ class SymmGroup:
             # tensor-core kernels it overlaps with.
             comm_blocks = int(os.environ.get("DTG_COMM_BLOCKS", 256 if self.world == 1 else 96))
         self.comm_blocks = min(comm_blocks, int(self.C.SYMM_MAX_CHANNELS))
-        self._peer_handles = []
         self.epoch = 0
-        # EXPERIMENTAL (DTG_NVLS=1): allocate through torch.distributed._symmetric_memory so every buffer is also
-        # bound to an NVSwitch multicast address; the bucket kernels then reduce in the switch (comm_nvls.cu).
-        self.nvls = bool(os.environ.get("DTG_NVLS")) and self.world > 1
+        self._chunks, self._n_chunks, self._cur, self._used = [], 0, None, 0
+        self.mode, self.multicast, self.comm, self.token = "local", False, None, ""
+        if self.world > 1:
+            # backend of the arena: VMM (fd export; + NVLS multicast when the fabric has it) or CUDA IPC
+            self.comm = _StoreComm(pg)
+            want = os.environ.get("DTG_SYMM", "vmm")
+            fd_ok, mc_ok = self.C.vmm_support(self.device.index or 0)
+            flags = self.comm.all_gather((bool(fd_ok) and want == "vmm", bool(mc_ok), os.getpid()))
+            self.mode = "vmm" if all(f[0] for f in flags) else "ipc"
+            self.multicast = (self.mode == "vmm" and all(f[1] for f in flags)
+                              and os.environ.get("DTG_NVLS", "1") != "0")
+            self.token = f"{flags[0][2]}-{self.comm.prefix.replace('/', '_')}"
+        # multimem kernels (in-switch reduction) for the bucket collectives whenever the arena is multicast-bound
+        self.nvls = self.multicast and os.environ.get("DTG_NVLS_KERNELS", "0") != "0"
         self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.pads = self.alloc_bytes(int(self.C.SYMM_PAD_BYTES))
         self.pad_ptrs = self.pads.ptrs
         _LIVE_GROUPS.append(self)
 
     # -- allocation -----------------------------------------------------------------------------
-    def _alloc_bytes_multicast(self, nbytes: int) -> SymmBuffer:
-        import torch.distributed._symmetric_memory as symm_mem
+    def _new_chunk(self, nbytes: int):
+        if self.world == 1:
+            ch = _IpcChunk(self, nbytes)
+        else:
+            ch = (_VmmChunk if self.mode == "vmm" else _IpcChunk)(self, nbytes)
+        self._n_chunks += 1
+        self._chunks.append(ch)
+        self._cur, self._used = ch, 0
+        return ch
 
-        pg = self.pg if self.pg is not None else dist.group.WORLD
-        try:
-            symm_mem.enable_symm_mem_for_group(pg.group_name)
-        except Exception:
-            pass  # newer torch enables groups on demand
-        raw = symm_mem.empty(int(nbytes), dtype=torch.uint8, device=self.device)
-        hdl = symm_mem.rendezvous(raw, pg)
-        ptrs = [int(p) for p in hdl.buffer_ptrs]
-        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
-        if mc == 0:
-            raise RuntimeError("DTG_NVLS=1 but this system exposes no NVSwitch multicast (NVLS) address")
-        raw.zero_()
-        return SymmBuffer(raw, ptrs, raw, mc_ptr=mc, handle=hdl)
+    def reserve(self, nbytes: int):
+        """Make room for ``nbytes`` of upcoming allocations in ONE chunk (one exchange) when the caller knows its
+        total up front (the data-parallel engines do: parameters + gradients)."""
+        if self.world > 1 and (self._cur is None or self._cur.size - self._used < nbytes):
+            self._new_chunk(int(nbytes) + self.ALIGN)
 
     def alloc_bytes(self, nbytes: int) -> SymmBuffer:
-        if self.nvls:
-            return self._alloc_bytes_multicast(nbytes)
-        raw, handle = self.C.symm_alloc(int(nbytes), self.device.index or 0)
+        n = _round_up(max(int(nbytes), 1), self.ALIGN)
         if self.world == 1:
-            ptrs = [raw.data_ptr()]
+            ch = self._new_chunk(n)     # one rank: nothing to exchange, plain allocations
+            off = 0
         else:
-            handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(handle), group=self.pg)
-            ptrs = []
-            for r, h in enumerate(handles):
-                if r == self.rank:
-                    ptrs.append(raw.data_ptr())
-                else:
-                    p = self.C.symm_open(h, self.device.index or 0)
-                    self._peer_handles.append(p)
-                    ptrs.append(p)
-            dist.barrier(group=self.pg)
-        return SymmBuffer(raw, ptrs, raw)
+            if self._cur is None or self._cur.size - self._used < n:
+                last = self._chunks[-1].size if self._chunks else 0
+                self._new_chunk(max(n, min(max(self.FIRST_CHUNK, 2 * last), self.MAX_GROWTH)))
+            ch, off = self._cur, self._used
+            self._used += n
+        raw = ch.local_view(off, n)
+        ptrs = [b + off for b in ch.bases]
+        return SymmBuffer(raw, ptrs, raw, mc_ptr=(ch.mc_base + off) if ch.mc_base else 0, handle=ch)
 
     def alloc(self, numel: int, dtype: torch.dtype) -> SymmBuffer:
         esize = torch.empty((), dtype=dtype).element_size()
@@ -141,6 +280,9 @@ class SymmGroup:
             return b.local
 
         return alloc
+
+    def reserved_bytes(self) -> int:
+        return sum(c.size for c in self._chunks)
 
     # -- collectives ------------------------------------------------------------------------------
     def _epochs(self, n: int = 2) -> int:
@@ -221,9 +363,11 @@ class SymmGroup:
             return f"(pad state unavailable: {e})"
 
     def close(self):
-        for p in self._peer_handles:
+        for c in self._chunks:
             try:
-                self.C.symm_close(p)
+                c.close()
             except Exception:
                 pass
-        self._peer_handles = []
+        self._chunks = []
+        if self in _LIVE_GROUPS:
+            _LIVE_GROUPS.remove(self)

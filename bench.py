@@ -220,6 +220,8 @@ def run_b200(args):
         faulthandler.register(signal.SIGTERM, file=sys.__stderr__, all_threads=True, chain=True)
     except Exception:
         pass
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")  # see distributed_training_guide_b200/__init__.py
     os.environ.setdefault("DTG_DIST_TIMEOUT_S", "150")       # a wedged collective aborts with a stack, well inside
     os.environ.setdefault("TORCH_NCCL_DUMP_ON_TIMEOUT", "1")  # the driver's per-N limit
     import torch

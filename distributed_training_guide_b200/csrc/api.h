@@ -45,6 +45,10 @@ void gemm_bf16_dist(int mode, const void* const* a_srcs, const void* const* b_sr
                     int K, long long lda, long long ldb, long long ldc, bool b_kmajor, bool accumulate, int nranks,
                     int rank, int rows_per_peer, cudaStream_t s);
 
+void gemm_bf16_bgather(const void* A, void* full_base, void* C, int M, int N, int K, long long lda, long long ldb,
+                       long long ldc, bool b_kmajor, const void* const* shards, long long per_bytes, long long w_off,
+                       long long w_bytes, uint32_t* counters, uint32_t target, int chunk_shift, uint32_t* const* pads,
+                       int nranks, int rank, uint32_t bar_epoch, cudaStream_t s);
 void gemm_bf16_ag(const void* const* a_bufs, const void* B, void* C, int M, int N, int K, long long ldb, long long ldc,
                   bool b_kmajor, int nranks, int rank, int rows_per_peer, uint32_t* flags, uint32_t ag_epoch,
                   uint32_t* const* pads, uint32_t bar_epoch, int n_comm, cudaStream_t s);

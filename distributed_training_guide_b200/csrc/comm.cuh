@@ -45,6 +45,8 @@ void comm_nvls_rs_adamw(const void* grads_mc, void* params_mc, const void* param
 
 // ---- fused_tp.cu / cross_entropy.cu helpers used by the tensor-parallel path ------------------------
 void tp_reduce_parts(const void* parts, const void* residual, void* out, long long n, int nparts, cudaStream_t s);
+void tp_reduce_mc(const void* part_mc, const void* residual, void* out, long long n, const SymmPads& pads, int rank,
+                  int nranks, uint32_t epoch, int* err, cudaStream_t s);
 void vp_ce_stats(const void* logits, const long long* targets, void* stats, int T, int Vl, int v0, cudaStream_t s);
 void vp_ce_grad(void* logits, const long long* targets, const SymmPtrs& stats, float* row_loss, const float* n_valid,
                 int T, int Vl, int v0, int nranks, cudaStream_t s);

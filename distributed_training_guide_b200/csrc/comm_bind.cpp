@@ -57,6 +57,15 @@ std::tuple<Tensor, py::bytes> symm_alloc(int64_t nbytes, int64_t device) {
   return {t, py::bytes(reinterpret_cast<const char*>(&h), sizeof(h))};
 }
 
+// An independent tensor (own version counter, own autograd identity) over bytes [off, off + nbytes) of a chunk
+// allocation; it keeps the chunk alive.  Sub-allocations must NOT be slices of one base tensor: an in-place write
+// to a gradient buffer would then bump the version of every parameter saved for backward.
+Tensor symm_alias(const Tensor& chunk, int64_t off, int64_t nbytes) {
+  TORCH_CHECK(chunk.scalar_type() == at::kByte && off >= 0 && nbytes >= 0 && off + nbytes <= chunk.numel(), "bad alias");
+  Tensor keep = chunk;
+  return torch::from_blob((char*)chunk.data_ptr() + off, {nbytes}, [keep](void*) {}, chunk.options());
+}
+
 uint64_t symm_open(const std::string& handle, int64_t device) {
   TORCH_CHECK(handle.size() == sizeof(cudaIpcMemHandle_t), "bad IPC handle size");
   const c10::cuda::CUDAGuard guard((c10::DeviceIndex)device);
@@ -165,6 +174,7 @@ void barrier(const std::vector<uint64_t>& pads, int64_t rank, int64_t epoch, con
 void bind_comm(pybind11::module_& m) {
   m.def("symm_alloc", &symm_alloc);
   m.def("symm_open", &symm_open);
+  m.def("symm_alias", &symm_alias);
   m.def("symm_close", &symm_close);
   m.def("symm_allocated_bytes", &symm_allocated_bytes);
   m.attr("SYMM_PAD_BYTES") = (int64_t)kPadBytes;

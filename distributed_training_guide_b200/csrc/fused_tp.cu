@@ -14,6 +14,7 @@
 //                        and the backward pulls its column slice of the peers' gradient shards.
 #include "api.h"
 #include "comm.cuh"
+#include "comm_device.cuh"
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -53,6 +54,50 @@ void tp_reduce_parts(const void* parts, const void* residual, void* out, long lo
   if (grid < 1) grid = 1;
   tp_reduce_parts_kernel<<<(int)grid, 256, 0, s>>>((const __nv_bfloat16*)parts, (const __nv_bfloat16*)residual,
                                                   (__nv_bfloat16*)out, nvec, nvec, nparts);
+  note_launch();
+  DTG_LAUNCH_CHECK();
+}
+
+// ---- GEMM -> reduce-scatter, reduce half on the NVSwitch ------------------------------------------------------
+// Every rank's row-parallel GEMM wrote its FULL partial [T, H] into its own copy of a multicast-bound symmetric
+// buffer (plain local stores: the GEMM epilogue is the un-distributed one).  This kernel is the whole rest of the
+// reduce-scatter: a device-side barrier at entry (every rank's GEMM has completed), then each 16-byte vector of MY
+// rows is read once through the multicast address with multimem.ld_reduce — the switch pulls the N copies and
+// adds them in fp32 — plus the residual, straight into the sequence-sharded output.  Versus the push variant
+// (GEMM pushes row chunks into N staging slots, barrier kernel, N-way sum kernel) that is one launch fewer, no
+// N-fold staging write + read in HBM, and 1/N of the NVLink ingress per GPU.
+__global__ void __launch_bounds__(kCommThreads) tp_reduce_mc_kernel(const char* __restrict__ part_mc,
+                                                                    const __nv_bfloat16* __restrict__ res,
+                                                                    __nv_bfloat16* __restrict__ out, long long nvec,
+                                                                    SymmPads pads, int rank, int nranks, uint32_t epoch,
+                                                                    int* err) {
+  symm_barrier(pads.ptr, rank, nranks, blockIdx.x, epoch, err);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    add8(acc, multimem_ld_reduce_bf16x8(part_mc + i * 16));
+    if (res) {
+      float f[8];
+      unpack8(ld8(res + i * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+    st8(out + i * 8, pack8(acc));
+  }
+}
+
+void tp_reduce_mc(const void* part_mc, const void* residual, void* out, long long n, const SymmPads& pads, int rank,
+                  int nranks, uint32_t epoch, int* err, cudaStream_t s) {
+  if (n % 8) throw std::runtime_error("tp_reduce_mc: size must be a multiple of 8");
+  if (part_mc == nullptr) throw std::runtime_error("tp_reduce_mc: no multicast address");
+  const long long nvec = n / 8;
+  long long grid = (nvec + kCommThreads - 1) / kCommThreads;
+  const long long cap = sm_count() < kMaxChannels ? sm_count() : kMaxChannels;   // one barrier channel per CTA
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  tp_reduce_mc_kernel<<<(int)grid, kCommThreads, 0, s>>>((const char*)part_mc, (const __nv_bfloat16*)residual,
+                                                       (__nv_bfloat16*)out, nvec, pads, rank, nranks, epoch, err);
   note_launch();
   DTG_LAUNCH_CHECK();
 }

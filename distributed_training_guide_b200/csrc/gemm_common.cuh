@@ -24,6 +24,9 @@ struct GemmCfg {
   static constexpr int STAGES = (CG == 1) ? 4 : 6;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
+  // B_MODE 3 (operand B gathered from the ranks' FSDP shards by warp 3 of every CTA): a 2-slot bounce ring
+  static constexpr int GATHER_PIECE = 16384;
+  static constexpr int GATHER_BYTES = 2 * GATHER_PIECE;
 };
 
 template <int N>
@@ -46,6 +49,20 @@ struct GemmDist {
   int n_comm;                        // clusters (CTA pairs) that copy instead of multiplying
   int rank, nranks;
   long long tile_bytes;              // bytes of one 256-row tile of A (contiguous: lda == K)
+  // B_MODE 3 (FSDP unshard inside the consuming GEMM): operand B is a weight whose bytes [bg_begin, bg_end) of the
+  // group's flat layout are spread over the ranks' shards (rank p owns flat bytes [p*per, (p+1)*per)).  Warp 3 of
+  // every CTA bounces 16 KB pieces shard -> smem -> local full buffer and counts them per `1 << bg_chunk_shift`
+  // byte chunk; the TMA producer acquires the counters of the chunks under a B box before loading it.
+  const char* bg_src[kMaxRanks];     // shard base per rank (NOT rotated; [rank] is my own shard)
+  char* bg_dst;                      // local full (unsharded) flat buffer of the group
+  long long bg_per_bytes;            // shard size in bytes
+  long long bg_begin, bg_end;        // flat byte range of B (piece aligned; chunk aligned at both ends)
+  uint32_t* bg_cnt;                  // one counter per chunk of the flat buffer (monotonic over generations)
+  uint32_t bg_target;                // counter value at which a chunk of this generation is complete
+  int bg_chunk_shift;                // log2(chunk bytes)
+  int bg_row_bytes;                  // bytes of one row of B as stored (ldb * 2)
+  int bg_rows;                       // rows of B as stored
+  int n_tile_shift;                  // rotate the N tile order so every rank starts on the rows it owns
   // L2-aware rasterisation of the plain GEMM: tiles run M-fastest inside groups of `group_m` row tiles (0 = one
   // group = the whole M extent); `num_n_tiles` is set by the launcher.
   int group_m, num_n_tiles;
@@ -76,7 +93,8 @@ __host__ __device__ __forceinline__ void tile_mn(int t, int num_m_tiles, const G
       return;
     }
     m = tile_m(t, num_m_tiles, d);
-    n = t / num_m_tiles;
+    n = t / num_m_tiles + d.n_tile_shift;
+    if (n >= d.num_n_tiles && d.n_tile_shift) n -= d.num_n_tiles;
     return;
   }
   const int num_n = d.k_shift;  // reused field: number of N tiles (K is never gathered in this mode)

@@ -42,6 +42,13 @@ using namespace ptx;
 //                    exactly once (peer memory bypasses the local L2, so mode 1 re-fetches it per N tile).
 //   C_MODE           0 = local C;  1 = each `rows_per_peer` row chunk of C is stored into its owner's
 //                    staging buffer (GEMM -> reduce-scatter push).
+// B_MODE 3: the gather starts at the first chunk of [bg_begin, bg_end) this rank owns (local copy, no NVLink latency)
+__device__ __forceinline__ int bg_rotation_chunks(const GemmDist& d) {
+  const long long mine = (long long)d.rank * d.bg_per_bytes;
+  if (mine <= d.bg_begin || mine >= d.bg_end) return 0;
+  return (int)((mine - d.bg_begin) >> d.bg_chunk_shift);
+}
+
 template <bool A_K, bool B_K, int CG, int A_MODE = 0, int B_MODE = 0, int C_MODE = 0>
 __global__ void __launch_bounds__(256, 1)
 gemm_bf16_kernel(const __grid_constant__ TmapSet<(A_MODE ? kMaxRanks : 1)> tmAs,
@@ -85,6 +92,8 @@ gemm_bf16_kernel(const __grid_constant__ TmapSet<(A_MODE ? kMaxRanks : 1)> tmAs,
     }
     if constexpr (A_MODE == 3)
       for (int i = 0; i < Cfg::STAGES; ++i) mbar_init(&comm_bar[i], 1);
+    if constexpr (B_MODE == 3)
+      for (int i = 0; i < 2; ++i) mbar_init(&comm_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -150,6 +159,36 @@ gemm_bf16_kernel(const __grid_constant__ TmapSet<(A_MODE ? kMaxRanks : 1)> tmAs,
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      // B_MODE 3: chunks of B complete (roughly) in the order the gather warps copy them — starting at my own shard.
+      // `bg_wm` = how many chunks, in that order, this CTA has already seen complete; a B box is readable once the
+      // watermark has passed the last chunk under its rows.  Every chunk counter is polled at most once per CTA.
+      [[maybe_unused]] int bg_wm = 0;
+      [[maybe_unused]] const int bg_nch = (B_MODE == 3) ? (int)((dist.bg_end - dist.bg_begin) >> dist.bg_chunk_shift) : 0;
+      [[maybe_unused]] const int bg_rot = (B_MODE == 3) ? bg_rotation_chunks(dist) : 0;
+      [[maybe_unused]] auto bg_wait_rows = [&](int r0, int r1) {   // rows [r0, r1) of B as stored
+        if (r1 > dist.bg_rows) r1 = dist.bg_rows;
+        if (r0 >= r1) return;
+        const int c0 = (int)(((long long)r0 * dist.bg_row_bytes) >> dist.bg_chunk_shift);
+        const int c1 = (int)((((long long)r1 * dist.bg_row_bytes) - 1) >> dist.bg_chunk_shift);
+        int need = 0;                                  // highest rotated index under the rows, + 1
+        for (int c = c0; c <= c1; ++c) {
+          int ci = c - bg_rot;
+          if (ci < 0) ci += bg_nch;
+          need = ci + 1 > need ? ci + 1 : need;
+        }
+        if (need <= bg_wm) return;
+        const uint32_t* cnt = dist.bg_cnt + (dist.bg_begin >> dist.bg_chunk_shift);
+        while (bg_wm < need) {
+          int c = bg_wm + bg_rot;
+          if (c >= bg_nch) c -= bg_nch;
+          const unsigned long long t0 = global_timer_ns();
+          while ((int32_t)(ld_acquire_gpu(cnt + c) - dist.bg_target) < 0)
+            if (global_timer_ns() - t0 > kWaitTimeoutNs)
+              wait_timeout_trap("FSDP gather GEMM: a weight chunk never arrived", __FILE__, __LINE__);
+          ++bg_wm;
+        }
+        fence_proxy_async_all();                       // the chunk was written through the async proxy (bulk stores)
+      };
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         int tm_, tn_;
         tile_mn(t, num_m_tiles, dist, local_m_tiles, tm_, tn_);
@@ -167,6 +206,7 @@ gemm_bf16_kernel(const __grid_constant__ TmapSet<(A_MODE ? kMaxRanks : 1)> tmAs,
             fence_proxy_async_all();
           }
         }
+        if constexpr (B_MODE == 3 && B_K) bg_wait_rows(nb, nb + Cfg::B_ROWS);   // forward: B rows are output features
         if constexpr (A_MODE == 1) {  // this row block lives on rank m0 / rows_per_peer
           const int peer = m0 / dist.rows_per_peer;
           tmA_p = &tmAs.m[peer];
@@ -174,7 +214,7 @@ gemm_bf16_kernel(const __grid_constant__ TmapSet<(A_MODE ? kMaxRanks : 1)> tmAs,
         }
         for (int kbi = 0; kbi < num_kb; ++kbi) {
           // K-gathered operands start with the local rank's slice of K
-          const int kb = (A_MODE == 2 || B_MODE == 2) ? (kbi + dist.k_shift) % num_kb : kbi;
+          const int kb = (A_MODE == 2 || B_MODE == 2 || (B_MODE == 3 && !B_K)) ? (kbi + dist.k_shift) % num_kb : kbi;
           const int k0 = kb * Cfg::BK;
           int a_k0 = k0, b_k0 = k0;
           const CUtensorMap* tmB_p = &tmBs.m[0];
@@ -188,6 +228,7 @@ gemm_bf16_kernel(const __grid_constant__ TmapSet<(A_MODE ? kMaxRanks : 1)> tmAs,
             tmB_p = &tmBs.m[peer];
             b_k0 = k0 - peer * dist.rows_per_peer;
           }
+          if constexpr (B_MODE == 3 && !B_K) bg_wait_rows(k0, k0 + Cfg::BK);      // dgrad: B rows are the reduction index
           const CUtensorMap& tmA = *tmA_p;
           const CUtensorMap& tmB = *tmB_p;
           mbar_wait(&empty[stage], phase ^ 1);
@@ -256,6 +297,68 @@ gemm_bf16_kernel(const __grid_constant__ TmapSet<(A_MODE ? kMaxRanks : 1)> tmAs,
         }
         if constexpr (CG == 1) mma_commit(&tmem_full[acc]); else mma_commit_cg2_mc(&tmem_full[acc], 0b11);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp == 3 && !is_comm) {
+    // ===================== B_MODE 3: gather warp (FSDP unshard inside the consuming GEMM) =====================
+    if constexpr (B_MODE == 3) {
+      if (elect_one()) {
+        constexpr uint32_t PIECE = Cfg::GATHER_PIECE;
+        uint8_t* gs = smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES;
+        const int ch = (int)blockIdx.x, nr = dist.nranks, rk = dist.rank;
+        // every rank's shard is final (its AdamW of the previous step joined the compute stream) once its copy of
+        // this kernel has started: signal on my channel, wait for the peers
+        for (int p = 0; p < nr; ++p) st_release_sys(dist.pads[p] + ch * kMaxRanks + rk, dist.bar_epoch);
+        for (int p = 0; p < nr; ++p) {
+          const uint32_t* mine = dist.pads[rk] + ch * kMaxRanks + p;
+          const unsigned long long t0 = global_timer_ns();
+          while ((int32_t)(ld_acquire_sys(mine) - dist.bar_epoch) < 0)
+            if (global_timer_ns() - t0 > kWaitTimeoutNs)
+              wait_timeout_trap("FSDP gather GEMM: peer did not arrive at the entry barrier", __FILE__, __LINE__);
+        }
+        const long long np = (dist.bg_end - dist.bg_begin) / PIECE;
+        const long long rot = (long long)bg_rotation_chunks(dist) << dist.bg_chunk_shift >> 14;   // in pieces
+        static_assert(PIECE == (1u << 14), "rotation shift assumes 16 KB pieces");
+        uint32_t* const cnt = dist.bg_cnt;
+        auto flat_of = [&](long long i) {
+          long long j = i + rot;
+          if (j >= np) j -= np;
+          return dist.bg_begin + j * (long long)PIECE;
+        };
+        auto issue = [&](long long i, uint32_t it) {
+          const long long flat = flat_of(i);
+          const int owner = (int)(flat / dist.bg_per_bytes);
+          const char* src = dist.bg_src[owner] + (flat - (long long)owner * dist.bg_per_bytes);
+          const uint32_t slot = it & 1;
+          mbar_arrive_expect_tx(&comm_bar[slot], PIECE);
+          bulk_load_g2s(gs + slot * PIECE, src, PIECE, &comm_bar[slot]);
+        };
+        const long long first = blockIdx.x, stride = gridDim.x;
+        uint32_t it = 0;
+        long long prev_flat = -1;
+        if (first < np) issue(first, 0);
+        for (long long i = first; i < np; i += stride, ++it) {
+          if (i + stride < np) {
+            bulk_wait_group_read<0>();   // the store that last read the other slot (piece it-1) is done with it
+            issue(i + stride, it + 1);
+          }
+          const uint32_t slot = it & 1;
+          mbar_wait(&comm_bar[slot], (it >> 1) & 1);
+          const long long flat = flat_of(i);
+          bulk_store_s2g(dist.bg_dst + flat, gs + slot * PIECE, PIECE);
+          bulk_commit_group();
+          if (prev_flat >= 0) {          // piece it-1 is complete in local memory once only this store is pending
+            bulk_wait_group<1>();
+            fence_proxy_async_all();
+            red_release_gpu_add(cnt + (prev_flat >> dist.bg_chunk_shift), 1u);
+          }
+          prev_flat = flat;
+        }
+        if (prev_flat >= 0) {
+          bulk_wait_group<0>();
+          fence_proxy_async_all();
+          red_release_gpu_add(cnt + (prev_flat >> dist.bg_chunk_shift), 1u);
+        }
       }
     }
   } else if (warp >= 4 && !is_comm) {
@@ -398,19 +501,20 @@ static void launch_gemm(const void* const* a_srcs, const void* const* b_srcs, vo
     const int ks = (A_MODE == 2) ? rpp : K;     // K extent of this source
     tmA.m[p] = A_K ? make_tmap_2d(a_srcs[p], ks, rows, lda * 2, 64, Cfg::BM) : make_tmap_2d(a_srcs[p], rows, ks, lda * 2, 64, 64);
   }
-  for (int p = 0; p < (B_MODE ? nranks : 1); ++p) {
+  for (int p = 0; p < ((B_MODE == 1 || B_MODE == 2) ? nranks : 1); ++p) {
     const int ks = (B_MODE == 2) ? rpp : K;
     tmB.m[p] = B_K ? make_tmap_2d(b_srcs[p], ks, N, ldb * 2, 64, Cfg::B_ROWS) : make_tmap_2d(b_srcs[p], N, ks, ldb * 2, 64, 64);
   }
   for (int p = ((A_MODE == 1 || A_MODE == 2) ? nranks : 1); p < (A_MODE ? kMaxRanks : 1); ++p) tmA.m[p] = tmA.m[0];
-  for (int p = (B_MODE ? nranks : 1); p < (B_MODE ? kMaxRanks : 1); ++p) tmB.m[p] = tmB.m[0];
+  for (int p = ((B_MODE == 1 || B_MODE == 2) ? nranks : 1); p < (B_MODE ? kMaxRanks : 1); ++p) tmB.m[p] = tmB.m[0];
   const int num_m_tiles = (M + Cfg::BM * CG - 1) / (Cfg::BM * CG);
   const int num_n_tiles = (N + Cfg::BN - 1) / Cfg::BN;
   const int num_tiles = num_m_tiles * num_n_tiles;
   auto kern = gemm_bf16_kernel<A_K, B_K, CG, A_MODE, B_MODE, C_MODE>;
+  constexpr int kSmem = Cfg::SMEM_BYTES + (B_MODE == 3 ? Cfg::GATHER_BYTES : 0);
   static bool attr_set = false;
   if (!attr_set) {
-    DTG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    DTG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_set = true;
   }
   dist.num_n_tiles = num_n_tiles;
@@ -438,7 +542,7 @@ static void launch_gemm(const void* const* a_srcs, const void* const* b_srcs, vo
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * CG);
   cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.dynamicSmemBytes = kSmem;
   cfg.stream = s;
   cudaLaunchAttribute attrs[1];
   attrs[0].id = cudaLaunchAttributeClusterDimension;
@@ -576,6 +680,56 @@ void gemm_bf16_ag(const void* const* a_bufs, const void* B, void* C, int M, int 
   const void* bs[1] = {B};
   if (b_kmajor) launch_gemm<true, true, 2, 3, 0, 0>(as, bs, C, M, N, K, K, ldb, ldc, false, dist, nranks, s);
   else launch_gemm<true, false, 2, 3, 0, 0>(as, bs, C, M, N, K, K, ldb, ldc, false, dist, nranks, s);
+}
+
+
+// FSDP unshard fused into the consuming GEMM (B_MODE 3): C[M,N] = A . op(B) where B is a weight of a flat parameter
+// group whose bytes are spread over the ranks' shards.  `full_base` is the local unsharded flat buffer of the group
+// (B = full_base + w_off bytes, row-major with leading dimension ldb); `shards[p]` rank p's shard (per_bytes each,
+// rank p owns flat bytes [p*per, (p+1)*per)).  The kernel's gather warps copy [w_off, w_off + w_bytes) out of the
+// shards into the full buffer while its tensor cores consume the rows that have already arrived.
+void gemm_bf16_bgather(const void* A, void* full_base, void* C, int M, int N, int K, long long lda, long long ldb,
+                       long long ldc, bool b_kmajor, const void* const* shards, long long per_bytes, long long w_off,
+                       long long w_bytes, uint32_t* counters, uint32_t target, int chunk_shift, uint32_t* const* pads,
+                       int nranks, int rank, uint32_t bar_epoch, cudaStream_t s) {
+  using Cfg = GemmCfg<2>;
+  if ((N % 8) || (ldc % 8) || (lda % 8) || (ldb % 8))
+    throw std::runtime_error("gemm_bf16_bgather: N and the leading dimensions must be multiples of 8 elements");
+  if (nranks < 1 || nranks > kMaxRanks) throw std::runtime_error("gemm_bf16_bgather: 1..8 ranks");
+  const long long chunk = 1LL << chunk_shift;
+  if (chunk < Cfg::GATHER_PIECE || (w_off % chunk) || (w_bytes % chunk) || (per_bytes % chunk))
+    throw std::runtime_error("gemm_bf16_bgather: weight offset / size / shard size must be multiples of the chunk size");
+  const int b_rows = b_kmajor ? N : K;                 // rows of B as stored
+  const int b_cols = b_kmajor ? K : N;
+  if (ldb != b_cols || (long long)b_rows * b_cols * 2 > w_bytes)
+    throw std::runtime_error("gemm_bf16_bgather: B must be a dense row-major weight inside the gathered range");
+  if (sm_count() > 256 /* kMaxChannels of the signal pad (comm.cuh) */) throw std::runtime_error("gemm_bf16_bgather: more CTAs than signal-pad channels");
+  GemmDist dist{};
+  for (int p = 0; p < nranks; ++p) {
+    dist.bg_src[p] = (const char*)shards[p];
+    dist.pads[p] = pads[p];
+  }
+  dist.bg_dst = (char*)full_base;
+  dist.bg_per_bytes = per_bytes;
+  dist.bg_begin = w_off;
+  dist.bg_end = w_off + w_bytes;
+  dist.bg_cnt = counters;
+  dist.bg_target = target;
+  dist.bg_chunk_shift = chunk_shift;
+  dist.bg_row_bytes = (int)(ldb * 2);
+  dist.bg_rows = b_rows;
+  dist.rank = rank;
+  dist.nranks = nranks;
+  dist.bar_epoch = bar_epoch;
+  // start on the rows this rank owns (their copy is local): rotate the N tiles (forward) / K blocks (dgrad)
+  long long my_row = ((long long)rank * per_bytes - w_off) / (ldb * 2);
+  if (my_row < 0 || my_row >= b_rows) my_row = 0;
+  if (b_kmajor) dist.n_tile_shift = (int)(my_row / Cfg::BN);
+  else dist.k_shift = (int)(my_row / Cfg::BK);
+  const void* as[1] = {A};
+  const void* bs[1] = {(const char*)full_base + w_off};
+  if (b_kmajor) launch_gemm<true, true, 2, 0, 3, 0>(as, bs, C, M, N, K, lda, ldb, ldc, false, dist, nranks, s);
+  else launch_gemm<true, false, 2, 0, 3, 0>(as, bs, C, M, N, K, lda, ldb, ldc, false, dist, nranks, s);
 }
 
 }  // namespace dtg

@@ -60,6 +60,36 @@ void py_gemm_ag(const std::vector<uint64_t>& a_bufs, const Tensor& b, Tensor& ou
                     (int)n_comm, stream());
 }
 
+// C = a @ op(B) with B = a weight inside the flat buffer `full` (element offset w_off, w_numel elements), gathered
+// from the ranks' shards by the kernel itself (FSDP unshard fused into the consuming GEMM)
+void py_gemm_bgather(const Tensor& a, Tensor& full, Tensor& out, bool b_kmajor, int64_t b_rows, int64_t b_cols,
+                     const std::vector<uint64_t>& shards, int64_t per_numel, int64_t w_off, int64_t w_numel,
+                     Tensor& counters, int64_t target, int64_t chunk_shift, const std::vector<uint64_t>& pads,
+                     int64_t rank, int64_t bar_epoch) {
+  TORCH_CHECK(a.is_cuda() && a.scalar_type() == at::kBFloat16 && a.dim() == 2 && a.stride(1) == 1, "bad A");
+  TORCH_CHECK(out.is_cuda() && out.scalar_type() == at::kBFloat16 && out.dim() == 2 && out.stride(1) == 1, "bad out");
+  TORCH_CHECK(full.is_contiguous() && full.scalar_type() == at::kBFloat16, "full must be the flat bf16 buffer");
+  TORCH_CHECK(counters.scalar_type() == at::kInt && counters.is_cuda(), "counters must be an int32 CUDA tensor");
+  TORCH_CHECK(w_off + w_numel <= full.numel() && b_rows * b_cols <= w_numel, "weight outside the flat buffer");
+  TORCH_CHECK(((int64_t)full.numel() * 2) >> chunk_shift <= counters.numel(), "counter array too small");
+  const c10::cuda::CUDAGuard guard(out.device());
+  const int nr = (int)shards.size();
+  TORCH_CHECK(nr == (int)pads.size() && nr <= kMaxRanks, "shards / pads per rank");
+  const int M = (int)out.size(0), N = (int)out.size(1);
+  const int K = (int)a.size(1);
+  TORCH_CHECK(a.size(0) == M && (b_kmajor ? (b_rows == N && b_cols == K) : (b_rows == K && b_cols == N)),
+              "shape mismatch");
+  const void* sh[kMaxRanks] = {nullptr};
+  uint32_t* pd[kMaxRanks] = {nullptr};
+  for (int i = 0; i < nr; ++i) {
+    sh[i] = (const void*)shards[i];
+    pd[i] = (uint32_t*)pads[i];
+  }
+  dtg::gemm_bf16_bgather(a.data_ptr(), full.data_ptr(), out.data_ptr(), M, N, K, a.stride(0), b_cols, out.stride(0),
+                         b_kmajor, sh, per_numel * 2, w_off * 2, w_numel * 2, (uint32_t*)counters.data_ptr<int>(),
+                         (uint32_t)target, (int)chunk_shift, pd, nr, (int)rank, (uint32_t)bar_epoch, stream());
+}
+
 void py_reduce_parts(const Tensor& parts, const c10::optional<Tensor>& residual, Tensor& out) {
   TORCH_CHECK(parts.is_contiguous() && out.is_contiguous() && parts.scalar_type() == at::kBFloat16, "bad tensors");
   const int64_t nparts = parts.size(0);
@@ -67,6 +97,19 @@ void py_reduce_parts(const Tensor& parts, const c10::optional<Tensor>& residual,
   const c10::cuda::CUDAGuard guard(out.device());
   dtg::tp_reduce_parts(parts.data_ptr(), residual.has_value() ? residual->data_ptr() : nullptr, out.data_ptr(),
                        out.numel(), (int)nparts, stream());
+}
+
+void py_reduce_mc(uint64_t part_mc, const c10::optional<Tensor>& residual, Tensor& out, const std::vector<uint64_t>& pads,
+                  int64_t rank, int64_t epoch, const c10::optional<Tensor>& err) {
+  TORCH_CHECK(out.is_contiguous() && out.scalar_type() == at::kBFloat16, "bad out");
+  TORCH_CHECK(!residual.has_value() || (residual->is_contiguous() && residual->numel() == out.numel()), "bad residual");
+  const c10::cuda::CUDAGuard guard(out.device());
+  SymmPads pd{};
+  TORCH_CHECK(pads.size() <= (size_t)kMaxRanks, "1..8 ranks supported");
+  for (size_t k = 0; k < pads.size(); ++k) pd.ptr[k] = (uint32_t*)pads[k];
+  dtg::tp_reduce_mc((const void*)part_mc, residual.has_value() ? residual->data_ptr() : nullptr, out.data_ptr(),
+                    out.numel(), pd, (int)rank, (int)pads.size(), (uint32_t)epoch,
+                    err.has_value() ? err->data_ptr<int>() : nullptr, stream());
 }
 
 void py_vp_ce_stats(const Tensor& logits, const Tensor& targets, Tensor& stats, int64_t v0) {
@@ -106,7 +149,9 @@ void py_embed_bwd(const Tensor& ids, const std::vector<uint64_t>& dx_ptrs, Tenso
 void bind_tp(pybind11::module_& m) {
   m.def("gemm_dist", &py_gemm_dist);
   m.def("gemm_ag", &py_gemm_ag);
+  m.def("gemm_bgather", &py_gemm_bgather);
   m.def("tp_reduce_parts", &py_reduce_parts);
+  m.def("tp_reduce_mc", &py_reduce_mc);
   m.def("vp_ce_stats", &py_vp_ce_stats);
   m.def("vp_ce_grad", &py_vp_ce_grad);
   m.def("tp_embed_fwd", &py_embed_fwd);

@@ -116,7 +116,7 @@ class _IpcChunk:
         self._C = C
 
     def local_view(self, off, n):
-        return self.raw[off:off + n]
+        return self._C.symm_alias(self.raw, int(off), int(n))   # NOT a slice: independent version counters
 
     def close(self):
         for p in self._opened:

@@ -62,7 +62,17 @@ class TPContext:
             # a rank writes its own rows, the all-gather->GEMM kernel fetches the others into the same slot and
             # the gathered copy is what the weight-gradient GEMM reads in backward (no second gather)
             self.act = symm.alloc((2 * n_layers + 1) * T * H, dtype)
-            self.stage = [symm.alloc(tp_size * Tl * H, dtype) for _ in range(2)]  # reduce-scatter landing zones
+            # GEMM -> reduce-scatter.  With an NVLS multicast binding: two [T, H] buffers the row-parallel GEMMs write
+            # their full partial into (local stores), reduced in the switch by the consumer (`reduce_scatter_partial`).
+            # Without: per-rank staging slots the GEMM epilogue pushes row chunks into.
+            self.mc_rs = bool(getattr(symm, "multicast", False)) and tp_size > 1 \
+                and os.environ.get("DTG_TP_RS", "mc") == "mc"
+            if self.mc_rs:
+                self.part = [symm.alloc(T * H, dtype) for _ in range(2)]
+                self._part_i = 0
+                self.stage = []
+            else:
+                self.stage = [symm.alloc(tp_size * Tl * H, dtype) for _ in range(2)]  # reduce-scatter landing zones
             self.gbuf = [symm.alloc(T * H, dtype) for _ in range(2)]             # gathered grads of row-parallel outputs
             self.flags = torch.zeros(max(1, T // 256), dtype=torch.int32, device=device)
             self.ag_epoch = 0
@@ -86,6 +96,30 @@ class TPContext:
         self.ag_epoch += 1
         self.symm.C.gemm_ag(bufs, b, out, b_kmajor, self.rank, self.rpp, self.flags, self.ag_epoch, self.symm.pad_ptrs,
                             self.symm._epochs(1), self.n_comm)
+
+    def row_parallel_gemm(self, a, w, trans_b, residual):
+        """reduce_scatter_rows(a @ op(w)) (+ residual) -> [T/t, H] for this rank (GPU kernels)."""
+        C = self.symm.C
+        T, Tl, H = a.shape[0], self.rpp, self.H
+        y = torch.empty(Tl, H, dtype=a.dtype, device=a.device)
+        if self.mc_rs:
+            # ONE plain tcgen05 GEMM into my copy of the partial buffer + ONE kernel that barriers and reads my
+            # rows through the multicast address (in-switch fp32 sum) fused with the residual add.  Two buffers
+            # alternate: a buffer is rewritten two GEMMs later, after a barrier every rank passed in between.
+            pb = self.part[self._part_i]
+            self._part_i ^= 1
+            ops.gemm(a, w, out=pb.local.view(T, H), trans_b=trans_b)
+            C.tp_reduce_mc(pb.mc_ptr + self.rank * Tl * H * 2, residual, y, self.symm.pad_ptrs, self.rank,
+                           self.symm._epochs(1), self.symm.err)
+            return y
+        st = self.next_stage()
+        my_slot = self.rank * Tl * H * 2
+        k = a.shape[1]
+        C.gemm_dist(2, [a.data_ptr()], [w.data_ptr()], [p + my_slot for p in st.ptrs], T, H, k, a.stride(0), w.stride(0),
+                    H, trans_b, False, self.t, self.rank, Tl)
+        self.barrier()
+        C.tp_reduce_parts(st.local.view(self.t, Tl, H), residual, y)
+        return y
 
     def next_stage(self):
         b = self.stage[self._stage_i]
@@ -164,15 +198,8 @@ class _ColumnParallelLinear(torch.autograd.Function):
         acc = owner._dtg_writes > 0
         owner._dtg_writes += 1
         ops.gemm(dy, full, out=gbuf, trans_a=True, accumulate=acc)
-        # dgrad: partial dx[T, H] = dy[T, n] @ W[n, H], pushed row-chunk-wise to the owners, then summed
-        st = tp.next_stage()
-        Tl = tp.rpp
-        my_slot = tp.rank * Tl * H * 2
-        C.gemm_dist(2, [dy.data_ptr()], [w.data_ptr()], [p + my_slot for p in st.ptrs], T, H, n, n, w.stride(0), H,
-                    False, False, tp.t, tp.rank, Tl)
-        tp.barrier()
-        dx = torch.empty(Tl, H, dtype=dy.dtype, device=dy.device)
-        C.tp_reduce_parts(st.local.view(tp.t, Tl, H), None, dx)
+        # dgrad: dx[T/t, H] = reduce_scatter_rows(dy[T, n] @ W[n, H])
+        dx = tp.row_parallel_gemm(dy, w, False, None)
         return dx, None, None, None, None
 
 
@@ -202,16 +229,7 @@ class _RowParallelLinear(torch.autograd.Function):
         if not tp.use_kernels:
             y = tp.reduce_scatter_rows(x @ w.t())
             return y + residual if residual is not None else y
-        C = _ext.load()
-        st = tp.next_stage()
-        Tl = tp.rpp
-        my_slot = tp.rank * Tl * H * 2
-        C.gemm_dist(2, [x.data_ptr()], [w.data_ptr()], [p + my_slot for p in st.ptrs], T, H, k, x.stride(0), w.stride(0),
-                    H, True, False, tp.t, tp.rank, Tl)
-        tp.barrier()
-        y = torch.empty(Tl, H, dtype=x.dtype, device=x.device)
-        C.tp_reduce_parts(st.local.view(tp.t, Tl, H), residual, y)
-        return y
+        return tp.row_parallel_gemm(x, w, True, residual)
 
     @staticmethod
     def backward(ctx, dy_local):

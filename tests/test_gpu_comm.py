@@ -116,6 +116,7 @@ def test_symmetric_collectives():
         assert r["allreduce_err"] < 0.05, r
         assert r["zero1_err"] < 0.05, r
         assert r["zero1_replica_diff"] == 0.0, r
+        assert r["reduce_mc_err"] < 0.02, r
         assert r["allgather_err"] == 0.0 and r["allgather_ce_err"] == 0.0, r
 
 
@@ -155,10 +156,11 @@ def test_ddp_zero1_gpu_matches_single_gpu():
 
 
 def _nvls_checks(rank, world):
-    """The same two checks as above through the NVSwitch-multicast kernels (DTG_NVLS=1, comm_nvls.cu)."""
+    """The same two checks as above through the NVSwitch-multicast kernels (comm_nvls.cu) on buffers from the own
+    VMM arena (csrc/symm_vmm.cpp: cuMemCreate + cuMulticastCreate/BindMem), plus the in-switch reduce-scatter."""
     import os
 
-    os.environ["DTG_NVLS"] = "1"
+    os.environ["DTG_NVLS_KERNELS"] = "1"
     import torch.distributed as dist
 
     from distributed_training_guide_b200.parallel import bootstrap
@@ -166,12 +168,11 @@ def _nvls_checks(rank, world):
 
     env = bootstrap.init_distributed("cuda")
     dev = env.device
-    try:
-        sg = SymmGroup(dev)
-    except Exception as e:  # no multicast support on this box / torch build
-        return {"skipped": f"{type(e).__name__}: {e}"}
-    assert sg.nvls and sg.pads.mc_ptr
-    out = {}
+    sg = SymmGroup(dev)
+    if not sg.multicast:
+        return {"skipped": f"no NVSwitch multicast on this system (arena mode {sg.mode})"}
+    assert sg.mode == "vmm" and sg.nvls and sg.pads.mc_ptr
+    out = {"mode": sg.mode, "chunks": sg._n_chunks}
     n = 8 * world * 12345
     torch.manual_seed(100 + rank)
     buf = sg.alloc(n, torch.bfloat16)
@@ -211,6 +212,21 @@ def _nvls_checks(rank, world):
     chk = p.local.float().clone()
     dist.broadcast(chk, src=0)
     out["zero1_replica_diff"] = (chk - p.local.float()).abs().max().item()
+    # ---- GEMM -> reduce-scatter, reduce half in the switch (fused_tp.cu: tp_reduce_mc) ------------------------------
+    Tl, H = 256, 512
+    part = sg.alloc(world * Tl * H, torch.bfloat16)
+    torch.manual_seed(300 + rank)
+    mine = torch.randn(world * Tl, H, device=dev).to(torch.bfloat16)
+    part.local.copy_(mine.reshape(-1))
+    res = torch.randn(Tl, H, device=dev).to(torch.bfloat16)
+    tot = mine.float().clone()
+    dist.all_reduce(tot)
+    want_rows = tot[rank * Tl:(rank + 1) * Tl] + res.float()
+    y = torch.empty(Tl, H, device=dev, dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    sg.C.tp_reduce_mc(part.mc_ptr + rank * Tl * H * 2, res, y, sg.pad_ptrs, rank, sg._epochs(1), sg.err)
+    torch.cuda.synchronize()
+    out["reduce_mc_err"] = ((y.float() - want_rows).abs().max() / want_rows.abs().max()).item()
     sg.check()
     return out
 
@@ -225,3 +241,4 @@ def test_nvls_collectives():
         assert r["allreduce_err"] < 0.05, r
         assert r["zero1_err"] < 0.05, r
         assert r["zero1_replica_diff"] == 0.0, r
+        assert r["reduce_mc_err"] < 0.02, r

@@ -156,6 +156,17 @@ void allgather(const std::vector<uint64_t>& shards, Tensor& full, const std::vec
                  (int)shards.size(), (uint32_t)epoch, err_ptr(err), barrier, (int)blocks, stream());
 }
 
+void gather_range(const std::vector<uint64_t>& shards, Tensor& full, const std::vector<uint64_t>& pads, int64_t begin,
+                  int64_t end, int64_t per, int64_t rank, int64_t epoch, const c10::optional<Tensor>& err, bool barrier) {
+  TORCH_CHECK(full.is_contiguous() && full.scalar_type() == at::kBFloat16, "full must be contiguous bf16");
+  TORCH_CHECK(0 <= begin && begin <= end && end <= full.numel(), "bad range");
+  SymmPtrs sp{};
+  TORCH_CHECK(shards.size() <= (size_t)kMaxRanks, "1..8 ranks supported");
+  for (size_t k = 0; k < shards.size(); ++k) sp.ptr[k] = (char*)shards[k];
+  comm_gather_range_ce(sp, full.data_ptr(), pads_of(pads), (size_t)begin, (size_t)end, (size_t)per, (int)rank,
+                       (int)shards.size(), (uint32_t)epoch, err_ptr(err), barrier, stream());
+}
+
 void reduce_scatter(const std::vector<uint64_t>& grads, Tensor& out, const std::vector<uint64_t>& pads, int64_t elem_off,
                     int64_t n, double scale, int64_t rank, int64_t epoch, const c10::optional<Tensor>& err,
                     int64_t blocks) {
@@ -185,6 +196,7 @@ void bind_comm(pybind11::module_& m) {
   m.def("comm_nvls_allreduce_scale", &nvls_allreduce_scale);
   m.def("comm_nvls_rs_adamw", &nvls_rs_adamw);
   m.def("comm_reduce_scatter", &reduce_scatter);
+  m.def("comm_gather_range", &gather_range);
   m.def("comm_barrier", &barrier);
 }
 }  // namespace dtg

@@ -112,7 +112,11 @@ class _Linear(torch.autograd.Function):
         ctx.save_for_backward(x2, w)
         ctx.w_param = w_param if w_param is not None else w
         ctx.x_shape = x.shape
-        y = gemm(x2, w, trans_b=True)
+        gs = getattr(ctx.w_param, "_dtg_gather", None)   # FSDP: the weight may still have to be gathered
+        if gs is not None and x2.is_cuda and gs.pending():
+            y = gs.gemm(x2 if x2.is_contiguous() else x2.contiguous(), True)   # unshard fused into this GEMM
+        else:
+            y = gemm(x2, w, trans_b=True)
         return y.view(*x.shape[:-1], w.shape[0])
 
     @staticmethod
@@ -123,7 +127,11 @@ class _Linear(torch.autograd.Function):
             dy2 = dy2.contiguous()
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = gemm(dy2, w).view(ctx.x_shape)  # [T,N] @ [N,K]
+            gs = getattr(ctx.w_param, "_dtg_gather", None)
+            if gs is not None and dy2.is_cuda and gs.pending():
+                dx = gs.gemm(dy2, False).view(ctx.x_shape)   # FSDP: re-gather the weight inside the dgrad GEMM
+            else:
+                dx = gemm(dy2, w).view(ctx.x_shape)  # [T,N] @ [N,K]
         dw = None
         if ctx.needs_input_grad[1] or getattr(ctx.w_param, "_dtg_grad", None) is not None:
             side = _WGRAD_SIDE["enabled"] and dy2.is_cuda and getattr(ctx.w_param, "_dtg_grad", None) is not None

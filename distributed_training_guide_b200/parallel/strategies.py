@@ -300,7 +300,8 @@ class FullyShardedDataParallel(Strategy):
         if env.device.type == "cuda":
             torch.cuda.synchronize()
         ckpt_utils.save_sharded(exp_dir, self.engine.sharded_state(), lr_scheduler, state, env.rank, ws,
-                                extra_rank0={"optimizer_steps.json": self.engine.optimizer_steps()})
+                                extra_rank0={"optimizer_steps.json": self.engine.optimizer_steps(),
+                                             "layout.json": self.engine.layout_description()})
         self.barrier()
 
     def load_checkpoint(self, exp_dir, model, optimizer, lr_scheduler):

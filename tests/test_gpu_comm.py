@@ -116,7 +116,6 @@ def test_symmetric_collectives():
         assert r["allreduce_err"] < 0.05, r
         assert r["zero1_err"] < 0.05, r
         assert r["zero1_replica_diff"] == 0.0, r
-        assert r["reduce_mc_err"] < 0.02, r
         assert r["allgather_err"] == 0.0 and r["allgather_ce_err"] == 0.0, r
 
 

@@ -130,23 +130,36 @@ def test_tensor_parallel_gpu_matches_single_gpu():
             assert abs(a - b) < 6e-2, (losses, ref)
 
 
-def _fsdp_train(rank, world, steps):
+def _fsdp_train(rank, world, steps, gather, ckpt_act):
+    import os
+
+    os.environ["DTG_FSDP_GATHER"] = gather
     from distributed_training_guide_b200.engine import TrainEngine
 
     torch.manual_seed(0)
-    eng = TrainEngine.create("debug-llama-gqa", parallelism="fsdp", batch_size=2, seq_length=256, lr=1e-3)
+    eng = TrainEngine.create("debug-llama-gqa", parallelism="fsdp", batch_size=2, seq_length=256, lr=1e-3,
+                             checkpoint_activations=ckpt_act, num_layers=5)   # 5 layers over 3 rotating slots:
+    # layers 0-1 are resharded after forward, so their dgrad GEMMs gather again
+    e = eng.strategy.engine
+    assert e.fused_gather == (gather == "gemm")
     losses = [float(eng.step(eng.synthetic_batch(seed=i))) for i in range(steps)]
+    n_fused = sum(getattr(e, "_ngather", {}).values())
+    sd = {k: v.float().cpu() for k, v in e.full_state_dict().items()}
     eng.close()
-    return losses
+    return losses, n_fused, sd
 
 
-def test_fsdp_gpu_matches_single_gpu():
+@pytest.mark.parametrize("gather,ckpt_act", [("gemm", False), ("gemm", True), ("ce", False)])
+def test_fsdp_gpu_matches_single_gpu(gather, ckpt_act):
+    """FSDP on 2 GPUs (unshard fused into the consuming GEMMs / copy-engine unshard) vs one GPU on the concatenated
+    batch: losses and the final weights."""
     from distributed_training_guide_b200.engine import TrainEngine
 
     steps, world = 3, 2
-    res = run_distributed(_fsdp_train, world=world, args=(steps,), timeout=300)
+    res = run_distributed(_fsdp_train, world=world, args=(steps, gather, ckpt_act), timeout=300)
     torch.manual_seed(0)
-    eng = TrainEngine.create("debug-llama-gqa", parallelism="single", batch_size=2, seq_length=256, lr=1e-3, device="cuda")
+    eng = TrainEngine.create("debug-llama-gqa", parallelism="single", batch_size=2, seq_length=256, lr=1e-3, device="cuda",
+                             num_layers=5)
     ref = []
     for i in range(steps):
         parts = []
@@ -155,5 +168,17 @@ def test_fsdp_gpu_matches_single_gpu():
             parts.append(torch.randint(0, eng.config.vocab_size, (2, 256), generator=g))
         ids = torch.cat(parts)
         ref.append(float(eng.step({"input_ids": ids, "labels": ids.clone()})))
+    ref_sd = {k: v.detach().float().cpu() for k, v in eng.model.state_dict().items()}
+    (l0, n0, sd0), (l1, n1, sd1) = res
     for i in range(steps):
-        assert abs(0.5 * (res[0][i] + res[1][i]) - ref[i]) < 6e-2, (i, res, ref)
+        assert abs(0.5 * (l0[i] + l1[i]) - ref[i]) < 6e-2, (i, l0, l1, ref)
+    if gather == "gemm":
+        # 5 layers x (qkv, o, gate_up, down) + lm_head in forward, + the resharded layers again in backward
+        assert n0 > steps * 21 and n0 == n1, (n0, n1)
+    else:
+        assert n0 == 0
+    import numpy as np
+
+    for k in sd0:
+        assert np.array_equal(sd0[k], sd1[k]), k
+        assert np.abs(sd0[k] - ref_sd[k].numpy()).max() < 3e-2, k

@@ -137,6 +137,25 @@ def prepare_assets(root: Path, model_name: str, seq_length: int, n_samples: int,
     return str(root / "model"), str(root / "data")
 
 
+def _environment_shims():
+    """Library-version glue OUTSIDE the reference tree (nothing under ``baseline/_ref`` is touched): the reference
+    was written against transformers 4.4x; this image ships 5.5, which dropped the per-instance
+    ``LlamaRotaryEmbedding.rope_init_fn`` attribute that chapter 04/05/07's ``reset_rope`` calls after
+    ``to_empty()``.  Restore it as a class attribute with the same contract ((config, device) -> (inv_freq, scaling))
+    so the unmodified scripts run; returns the list of shims applied (reported in the JSON line)."""
+    applied = []
+    try:
+        from transformers.models.llama.modeling_llama import LlamaRotaryEmbedding
+
+        if not hasattr(LlamaRotaryEmbedding, "rope_init_fn") and hasattr(LlamaRotaryEmbedding,
+                                                                         "compute_default_rope_parameters"):
+            LlamaRotaryEmbedding.rope_init_fn = staticmethod(LlamaRotaryEmbedding.compute_default_rope_parameters)
+            applied.append("transformers>=5: LlamaRotaryEmbedding.rope_init_fn -> compute_default_rope_parameters")
+    except Exception as e:  # pragma: no cover - depends on the installed transformers
+        applied.append(f"rope shim failed: {type(e).__name__}")
+    return applied
+
+
 # ---------------------------------------------------------------------------------------------
 # run + time
 # ---------------------------------------------------------------------------------------------
@@ -179,8 +198,10 @@ def run_reference(parallelism: str, model_name: str, gpus: int, steps: int, warm
 
     dp = world if parallelism in ("ddp", "fsdp", "single") else 1
     if parallelism == "2d":
-        dp = max(1, world // 4)
+        tp = int(extra_args[extra_args.index("-tp") + 1]) if "-tp" in extra_args else 4
+        dp = max(1, world // tp)
     n_samples = (steps + warmup) * dp * batch_size
+    extra_args = list(extra_args)
     model_dir, data_dir = prepare_assets(root, model_name, seq_length, n_samples, rank, num_layers)
 
     script = REF_DIR / CHAPTER_SCRIPTS[parallelism]
@@ -193,6 +214,7 @@ def run_reference(parallelism: str, model_name: str, gpus: int, steps: int, warm
     if not any(isinstance(h, logging.StreamHandler) for h in root_logger.handlers):
         root_logger.addHandler(logging.StreamHandler(sys.stderr))
 
+    shims = _environment_shims()
     old_argv, old_cwd = sys.argv, os.getcwd()
     sys.argv = argv
     os.chdir(script.parent)
@@ -232,6 +254,7 @@ def run_reference(parallelism: str, model_name: str, gpus: int, steps: int, warm
         "last_loss": timed[-1].get("running_loss"),
         "dp_size": dp,
         "install": how,
+        "environment_shims": shims,
         "script": CHAPTER_SCRIPTS[parallelism],
     }
     if dist.is_available() and dist.is_initialized():

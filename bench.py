@@ -99,6 +99,19 @@ def parse_args():
     return ap.parse_args()
 
 
+L2_NOTE = "per-step working set (>50 GB of weights/grads/activations) far exceeds the 126 MB L2"
+
+
+def _config(args, dp, tp, par):
+    """The benchmark configuration, IDENTICAL for both arms (the driver compares the dicts): what is computed, not
+    how.  Implementation details of an arm go under the top-level "engine" key."""
+    strat = {"ddp": "ddp+zero1", "fsdp": "fsdp", "tp": "tp", "2d": "fsdp x tp"}[par]
+    mesh = f"dp{dp}" if tp == 1 else f"dp{dp}xtp{tp}"
+    return {"model": args.model + (f"[layers={args.layers}]" if args.layers else ""),
+            "global_batch": dp * args.batch, "seq_len": args.seq_len, "parallelism": f"{mesh} ({strat})",
+            "optimizer": "AdamW, bf16 parameters and states", "l2": L2_NOTE}
+
+
 def _dist_max(x: float, device) -> float:
     import torch
     import torch.distributed as dist
@@ -320,11 +333,8 @@ def run_b200(args):
         "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic tokens, random-init weights",
         "impl": "b200",
-        "config": {"model": args.model + (f"[layers={args.layers}]" if args.layers else ""),
-                   "global_batch": dp * args.batch, "seq_len": args.seq_len,
-                   "parallelism": par_str + (f" ({pname}+zero1)" if par == "ddp" and world > 1 else f" ({pname})"),
-                   "optimizer": "AdamW bf16 states (as reference)",
-                   "l2": "per-step working set (>50 GB of weights/grads/activations) far exceeds the 126 MB L2"},
+        "config": _config(args, dp, tp, args.parallelism),
+        "engine": f"{par_str} ({pname}): distributed_training_guide_b200 {type(eng.strategy).__name__}",
         "clocks": clocks.summary(),
         "e2e": {"value": 1000.0 * tokens / ms_e2e, "unit": "tokens/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
@@ -356,8 +366,12 @@ def run_reference(args):
         world = int(os.environ.get("WORLD_SIZE", "1"))
         par = args.parallelism if world > 1 or args.parallelism != "ddp" else "ddp"
         extra = []
+        tp_ref = 1
         if par == "2d":
-            extra = ["-tp", str(args.tensor_parallel or 4)]
+            tp_ref = min(world, args.tensor_parallel or 4)
+            extra = ["-tp", str(tp_ref)]
+        elif par == "tp":
+            tp_ref = world
         r = run_ref.run_reference(par, args.model, args.gpus, args.steps, args.warmup, args.seq_len, args.batch,
                                   num_layers=args.layers, extra_args=extra)
     except Exception as e:  # the contract: never crash the driver on the reference arm
@@ -371,9 +385,8 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic tokens, random-init weights",
             "impl": "reference",
-            "config": {"model": args.model + (f"[layers={args.layers}]" if args.layers else ""),
-                       "global_batch": r["dp_size"] * args.batch, "seq_len": args.seq_len,
-                       "parallelism": f"dp{r['dp_size']} ({r['script']})"},
+            "config": _config(args, r["dp_size"], tp_ref, args.parallelism),
+            "engine": f"unmodified reference script {r['script']}", "environment_shims": r.get("environment_shims", []),
             "e2e": {"value": r["tokens_per_s"], "unit": "tokens/s", "h2d_bytes_per_step": tokens_bytes,
                     "d2h_bytes_per_step": 4,
                     "note": "the reference loop copies each batch H2D and reads loss.item() every step"},

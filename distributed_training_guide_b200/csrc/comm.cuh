@@ -40,8 +40,8 @@ void comm_barrier(const SymmPads& pads, int rank, int nranks, uint32_t epoch, in
 // NVLS (multicast) variants, comm_nvls.cu: `mc` = the buffer's multicast address
 void comm_nvls_allreduce_scale(void* mc, const SymmPads& pads, size_t elem_off, size_t n, float scale, int rank,
                                int nranks, uint32_t epoch, int* err, int blocks, cudaStream_t s);
-void comm_nvls_rs_adamw(const void* grads_mc, void* params_mc, const void* params_local, void* m, void* v,
-                        bool state_fp32, const SymmPads& pads, size_t elem_off, size_t n, const AdamWHyper& hp, int rank,
+void comm_nvls_rs_adamw(const void* grads_mc, void* params_mc, void* params_local, void* m, void* v, bool state_fp32,
+                        bool push_params, const SymmPads& pads, size_t elem_off, size_t n, const AdamWHyper& hp, int rank,
                         int nranks, uint32_t epoch, int* err, int blocks, cudaStream_t s);
 
 

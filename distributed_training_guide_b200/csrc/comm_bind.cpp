@@ -128,7 +128,7 @@ void nvls_allreduce_scale(uint64_t mc, const std::vector<uint64_t>& pads, int64_
                             (int)pads.size(), (uint32_t)epoch, err_ptr(err), (int)blocks, stream());
 }
 
-void nvls_rs_adamw(uint64_t grads_mc, uint64_t params_mc, uint64_t params_local, Tensor& m, Tensor& v,
+void nvls_rs_adamw(uint64_t grads_mc, uint64_t params_mc, uint64_t params_local, Tensor& m, Tensor& v, bool push_params,
                    const std::vector<uint64_t>& pads, int64_t elem_off, int64_t n, double lr, double b1, double b2,
                    double eps, double wd, int64_t step, double grad_scale, int64_t rank, int64_t epoch,
                    const c10::optional<Tensor>& err, int64_t blocks) {
@@ -137,9 +137,9 @@ void nvls_rs_adamw(uint64_t grads_mc, uint64_t params_mc, uint64_t params_local,
   const int nr = (int)pads.size();
   TORCH_CHECK(m.numel() * nr == n && v.numel() * nr == n, "optimizer shard must hold n / nranks elements");
   AdamWHyper hp = make_adamw_hyper((float)lr, (float)b1, (float)b2, (float)eps, (float)wd, (int)step, (float)grad_scale);
-  comm_nvls_rs_adamw((const void*)grads_mc, (void*)params_mc, (const void*)params_local, m.data_ptr(), v.data_ptr(), fp32,
-                     pads_of(pads), (size_t)elem_off, (size_t)n, hp, (int)rank, nr, (uint32_t)epoch, err_ptr(err),
-                     (int)blocks, stream());
+  comm_nvls_rs_adamw((const void*)grads_mc, (void*)params_mc, (void*)params_local, m.data_ptr(), v.data_ptr(), fp32,
+                     push_params, pads_of(pads), (size_t)elem_off, (size_t)n, hp, (int)rank, nr, (uint32_t)epoch,
+                     err_ptr(err), (int)blocks, stream());
 }
 
 void allgather(const std::vector<uint64_t>& shards, Tensor& full, const std::vector<uint64_t>& pads, int64_t shard_off,

@@ -42,10 +42,12 @@ __global__ void __launch_bounds__(kCommThreads) nvls_allreduce_scale_kernel(char
   symm_barrier(pads.ptr, rank, nranks, blockIdx.x, epoch + 1, err);
 }
 
-// ZeRO-1 bucket: in-switch reduce-scatter -> AdamW on my shard -> multicast the new parameters to every replica
-template <typename StateT>
+// ZeRO-1 bucket (PUSH): in-switch reduce-scatter -> AdamW on my shard -> multicast the new parameters to every replica.
+// FSDP (!PUSH): in-switch reduce-scatter -> AdamW on my parameter shard, which stays sharded (`params_local` is then
+// the shard buffer, indexed from 0, and `params_mc` is unused).
+template <typename StateT, bool PUSH>
 __global__ void __launch_bounds__(kCommThreads) nvls_rs_adamw_kernel(const char* grads_mc, char* params_mc,
-                                                                     const char* params_local, StateT* m, StateT* v,
+                                                                     char* params_local, StateT* m, StateT* v,
                                                                      SymmPads pads, size_t elem_off, size_t n,
                                                                      AdamWHyper hp, int rank, int nranks, uint32_t epoch,
                                                                      int* err) {
@@ -56,14 +58,16 @@ __global__ void __launch_bounds__(kCommThreads) nvls_rs_adamw_kernel(const char*
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
     float g[8], p[8], fm[8], fv[8];
     unpack_u4(multimem_ld_reduce_bf16x8(grads_mc + base + i * 16), g);
-    unpack8(ld8(reinterpret_cast<const __nv_bfloat16*>(params_local + base) + i * 8), p);
+    __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(PUSH ? params_local + base : params_local) + i * 8;
+    unpack8(ld8(pl), p);
     load_state8(m + i * 8, fm);
     load_state8(v + i * 8, fv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) adamw_update(p[j], g[j], fm[j], fv[j], hp);  // hp.grad_scale carries 1/N
     store_state8(m + i * 8, fm);
     store_state8(v + i * 8, fv);
-    multimem_st_v4(params_mc + base + i * 16, pack8_u4(p));
+    if (PUSH) multimem_st_v4(params_mc + base + i * 16, pack8_u4(p));
+    else *reinterpret_cast<uint4*>(pl) = pack8_u4(p);
   }
   symm_barrier(pads.ptr, rank, nranks, blockIdx.x, epoch + 1, err);
 }
@@ -83,19 +87,21 @@ void comm_nvls_allreduce_scale(void* mc, const SymmPads& pads, size_t elem_off, 
   DTG_LAUNCH_CHECK();
 }
 
-void comm_nvls_rs_adamw(const void* grads_mc, void* params_mc, const void* params_local, void* m, void* v,
-                        bool state_fp32, const SymmPads& pads, size_t elem_off, size_t n, const AdamWHyper& hp, int rank,
+void comm_nvls_rs_adamw(const void* grads_mc, void* params_mc, void* params_local, void* m, void* v, bool state_fp32,
+                        bool push_params, const SymmPads& pads, size_t elem_off, size_t n, const AdamWHyper& hp, int rank,
                         int nranks, uint32_t epoch, int* err, int blocks, cudaStream_t s) {
   check_nvls(n, nranks, blocks, grads_mc);
-  check_nvls(n, nranks, blocks, params_mc);
-  if (state_fp32)
-    nvls_rs_adamw_kernel<float><<<blocks, kCommThreads, 0, s>>>((const char*)grads_mc, (char*)params_mc,
-                                                                (const char*)params_local, (float*)m, (float*)v, pads,
-                                                                elem_off, n, hp, rank, nranks, epoch, err);
-  else
-    nvls_rs_adamw_kernel<__nv_bfloat16><<<blocks, kCommThreads, 0, s>>>(
-        (const char*)grads_mc, (char*)params_mc, (const char*)params_local, (__nv_bfloat16*)m, (__nv_bfloat16*)v, pads,
-        elem_off, n, hp, rank, nranks, epoch, err);
+  if (push_params) check_nvls(n, nranks, blocks, params_mc);
+#define LAUNCH_NVLS(ST, PUSH)                                                                                         \
+  nvls_rs_adamw_kernel<ST, PUSH><<<blocks, kCommThreads, 0, s>>>((const char*)grads_mc, (char*)params_mc,             \
+                                                                 (char*)params_local, (ST*)m, (ST*)v, pads, elem_off, \
+                                                                 n, hp, rank, nranks, epoch, err)
+  if (state_fp32) {
+    if (push_params) LAUNCH_NVLS(float, true); else LAUNCH_NVLS(float, false);
+  } else {
+    if (push_params) LAUNCH_NVLS(__nv_bfloat16, true); else LAUNCH_NVLS(__nv_bfloat16, false);
+  }
+#undef LAUNCH_NVLS
   note_launch();
   DTG_LAUNCH_CHECK();
 }

@@ -42,11 +42,13 @@ using namespace ptx;
 //                    exactly once (peer memory bypasses the local L2, so mode 1 re-fetches it per N tile).
 //   C_MODE           0 = local C;  1 = each `rows_per_peer` row chunk of C is stored into its owner's
 //                    staging buffer (GEMM -> reduce-scatter push).
-// B_MODE 3: the gather starts at the first chunk of [bg_begin, bg_end) this rank owns (local copy, no NVLink latency)
-__device__ __forceinline__ int bg_rotation_chunks(const GemmDist& d) {
-  const long long mine = (long long)d.rank * d.bg_per_bytes;
-  if (mine <= d.bg_begin || mine >= d.bg_end) return 0;
-  return (int)((mine - d.bg_begin) >> d.bg_chunk_shift);
+// B_MODE 3 helpers.  Chunks are waited for in the order the gather warps fetch them: the chunks behind my own slice
+// of [bg_begin, bg_end) first, then the ones in front of it; my own chunks are local and never waited for.
+__device__ __forceinline__ long long bg_clamp(const GemmDist& d, long long x) {
+  return x < d.bg_begin ? d.bg_begin : (x > d.bg_end ? d.bg_end : x);
+}
+__device__ __forceinline__ int bg_rotation_chunks(const GemmDist& d) {   // first chunk (relative) behind my slice
+  return (int)((bg_clamp(d, (long long)(d.rank + 1) * d.bg_per_bytes) - d.bg_begin) >> d.bg_chunk_shift);
 }
 
 template <bool A_K, bool B_K, int CG, int A_MODE = 0, int B_MODE = 0, int C_MODE = 0>
@@ -165,22 +167,24 @@ gemm_bf16_kernel(const __grid_constant__ TmapSet<(A_MODE ? kMaxRanks : 1)> tmAs,
       [[maybe_unused]] int bg_wm = 0;
       [[maybe_unused]] const int bg_nch = (B_MODE == 3) ? (int)((dist.bg_end - dist.bg_begin) >> dist.bg_chunk_shift) : 0;
       [[maybe_unused]] const int bg_rot = (B_MODE == 3) ? bg_rotation_chunks(dist) : 0;
+      [[maybe_unused]] const int bg_my0 = (B_MODE == 3)
+          ? (int)((bg_clamp(dist, (long long)dist.rank * dist.bg_per_bytes) - dist.bg_begin) >> dist.bg_chunk_shift) : 0;
+      [[maybe_unused]] const int bg_tail = bg_nch - bg_rot;          // remote chunks behind my slice: fetched first
       [[maybe_unused]] auto bg_wait_rows = [&](int r0, int r1) {   // rows [r0, r1) of B as stored
         if (r1 > dist.bg_rows) r1 = dist.bg_rows;
         if (r0 >= r1) return;
         const int c0 = (int)(((long long)r0 * dist.bg_row_bytes) >> dist.bg_chunk_shift);
         const int c1 = (int)((((long long)r1 * dist.bg_row_bytes) - 1) >> dist.bg_chunk_shift);
-        int need = 0;                                  // highest rotated index under the rows, + 1
+        int need = 0;                                  // highest fetch-order index under the rows, + 1
         for (int c = c0; c <= c1; ++c) {
-          int ci = c - bg_rot;
-          if (ci < 0) ci += bg_nch;
+          if (c >= bg_my0 && c < bg_rot) continue;     // my own chunk: already local
+          const int ci = c >= bg_rot ? c - bg_rot : bg_tail + c;
           need = ci + 1 > need ? ci + 1 : need;
         }
         if (need <= bg_wm) return;
         const uint32_t* cnt = dist.bg_cnt + (dist.bg_begin >> dist.bg_chunk_shift);
         while (bg_wm < need) {
-          int c = bg_wm + bg_rot;
-          if (c >= bg_nch) c -= bg_nch;
+          const int c = bg_wm < bg_tail ? bg_rot + bg_wm : bg_wm - bg_tail;
           const unsigned long long t0 = global_timer_ns();
           while ((int32_t)(ld_acquire_gpu(cnt + c) - dist.bg_target) < 0)
             if (global_timer_ns() - t0 > kWaitTimeoutNs)
@@ -306,24 +310,30 @@ gemm_bf16_kernel(const __grid_constant__ TmapSet<(A_MODE ? kMaxRanks : 1)> tmAs,
         constexpr uint32_t PIECE = Cfg::GATHER_PIECE;
         uint8_t* gs = smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES;
         const int ch = (int)blockIdx.x, nr = dist.nranks, rk = dist.rank;
-        // every rank's shard is final (its AdamW of the previous step joined the compute stream) once its copy of
-        // this kernel has started: signal on my channel, wait for the peers
-        for (int p = 0; p < nr; ++p) st_release_sys(dist.pads[p] + ch * kMaxRanks + rk, dist.bar_epoch);
-        for (int p = 0; p < nr; ++p) {
+        // Optional entry barrier (bar_epoch != 0): every peer has started its copy of this kernel.  The FSDP engine
+        // does not need it: shards only change inside the fused reduce-scatter+AdamW kernels, whose exit barrier
+        // every rank's compute stream joins before the next step's first GEMM.
+        for (int p = 0; p < nr && dist.bar_epoch; ++p)
+          st_release_sys(dist.pads[p] + ch * kMaxRanks + rk, dist.bar_epoch);
+        for (int p = 0; p < nr && dist.bar_epoch; ++p) {
           const uint32_t* mine = dist.pads[rk] + ch * kMaxRanks + p;
           const unsigned long long t0 = global_timer_ns();
           while ((int32_t)(ld_acquire_sys(mine) - dist.bar_epoch) < 0)
             if (global_timer_ns() - t0 > kWaitTimeoutNs)
               wait_timeout_trap("FSDP gather GEMM: peer did not arrive at the entry barrier", __FILE__, __LINE__);
         }
-        const long long np = (dist.bg_end - dist.bg_begin) / PIECE;
-        const long long rot = (long long)bg_rotation_chunks(dist) << dist.bg_chunk_shift >> 14;   // in pieces
-        static_assert(PIECE == (1u << 14), "rotation shift assumes 16 KB pieces");
+        // pieces of [bg_begin, bg_end) that live on OTHER ranks, visited starting right after my own slice (the
+        // local slice was copied into the full buffer before this kernel started: engine-side D2D prefetch)
+        static_assert(PIECE == (1u << 14), "16 KB pieces");
+        const long long my_lo = bg_clamp(dist, (long long)rk * dist.bg_per_bytes);
+        const long long my_hi = bg_clamp(dist, (long long)(rk + 1) * dist.bg_per_bytes);
+        const long long total = (dist.bg_end - dist.bg_begin) / PIECE;
+        const long long mine = (my_hi - my_lo) / PIECE;
+        const long long np = total - mine;                               // remote pieces
+        const long long after = (dist.bg_end - my_hi) / PIECE;           // remote pieces behind my slice
         uint32_t* const cnt = dist.bg_cnt;
-        auto flat_of = [&](long long i) {
-          long long j = i + rot;
-          if (j >= np) j -= np;
-          return dist.bg_begin + j * (long long)PIECE;
+        auto flat_of = [&](long long i) {                                // i-th remote piece in visiting order
+          return i < after ? my_hi + i * (long long)PIECE : dist.bg_begin + (i - after) * (long long)PIECE;
         };
         auto issue = [&](long long i, uint32_t it) {
           const long long flat = flat_of(i);

@@ -312,7 +312,7 @@ class FSDPEngine:
         with nvtx_range(f"gather_gemm:{g.name}"):
             C.gemm_bgather(a, full, out, b_kmajor, sp.rows, sp.cols, self._symm_of[sh.param.data_ptr()].ptrs,
                            sh.padded_numel, sp.off, sp.numel, self._counters[full.data_ptr()], n * ppc, shift,
-                           self.gather_pads.ptrs, self.rank, self.gather_pads.next_epoch())
+                           self.gather_pads.ptrs, self.rank, 0)   # epoch 0: no entry barrier (see the kernel)
         g._gathered.add(sp.off)
         return out
 
@@ -373,9 +373,17 @@ class FSDPEngine:
             t0 = self._trace_begin()
             with nvtx_range(f"unshard:{g.name}"):
                 if lazy:
+                    # what the GEMMs do not fetch themselves: my own slice (a local copy) and the small tail
+                    per = sh.padded_numel
+                    g.param[self.rank * per:(self.rank + 1) * per].copy_(sh.param, non_blocking=True)
+                    # the device barrier in front of the tail copies is also what orders every later read of the
+                    # peers' shards (by the gather warps of this group's GEMMs, which wait for `ag_done`) behind
+                    # the peers' previous optimizer work on their communication streams
                     if g.tail is not None:
                         self.symm.gather_range_(self._symm_of[sh.param.data_ptr()], g.param, g.tail[0], g.tail[1],
                                                 sh.padded_numel)
+                    else:
+                        self.symm.barrier_()
                 else:
                     if getattr(g, "chunk_bytes", 0):
                         g._gathered = {"all"}

@@ -226,7 +226,7 @@ class SymmGroup:
                               and os.environ.get("DTG_NVLS", "1") != "0")
             self.token = f"{flags[0][2]}-{self.comm.prefix.replace('/', '_')}"
         # multimem kernels (in-switch reduction) for the bucket collectives whenever the arena is multicast-bound
-        self.nvls = self.multicast and os.environ.get("DTG_NVLS_KERNELS", "0") != "0"
+        self.nvls = self.multicast and os.environ.get("DTG_NVLS_KERNELS", "1") != "0"
         self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.pads = self.alloc_bytes(int(self.C.SYMM_PAD_BYTES))
         self.pad_ptrs = self.pads.ptrs
@@ -318,10 +318,12 @@ class SymmGroup:
     def rs_adamw_(self, grads: SymmBuffer, params: Optional[SymmBuffer], param_local, m, v, push_params: bool,
                   elem_off: int, n: int, hyper, step: int, grad_scale: float, blocks: Optional[int] = None):
         lr, b1, b2, eps, wd = hyper
-        if self.nvls and push_params and grads.mc_ptr and params is not None and params.mc_ptr:
-            self.C.comm_nvls_rs_adamw(grads.mc_ptr, params.mc_ptr, params.ptrs[self.rank], m, v, self.pad_ptrs, elem_off,
-                                      n, lr, b1, b2, eps, wd, step, grad_scale, self.rank, self._epochs(2), self.err,
-                                      blocks or self.comm_blocks)
+        if self.nvls and grads.mc_ptr and (not push_params or (params is not None and params.mc_ptr)):
+            # in-switch reduction of the gradient slice (+ multicast of the new parameters for ZeRO-1)
+            self.C.comm_nvls_rs_adamw(grads.mc_ptr, params.mc_ptr if push_params else 0,
+                                      params.ptrs[self.rank] if push_params else param_local.data_ptr(), m, v,
+                                      push_params, self.pad_ptrs, elem_off, n, lr, b1, b2, eps, wd, step, grad_scale,
+                                      self.rank, self._epochs(2), self.err, blocks or self.comm_blocks)
             return
         self.C.comm_rs_adamw(grads.ptrs, params.ptrs if params is not None else [], param_local, m, v, push_params,
                              self.pad_ptrs, elem_off, n, lr, b1, b2, eps, wd, step, grad_scale, self.rank,

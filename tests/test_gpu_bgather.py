@@ -47,6 +47,7 @@ def _check(rank, world):
     ppc = (1 << shift) // 16384
     for gen in (1, 2):                          # two generations: counters are monotonic
         full.zero_()
+        full[rank * per:(rank + 1) * per].copy_(shard.local)   # the local slice is the caller's job (a D2D copy)
         y = torch.empty(M, N1, device=dev, dtype=torch.bfloat16)
         C.gemm_bgather(x, full, y, True, N1, K1, shard.ptrs, per, 0, n1, counters, gen * ppc, shift, sg.pad_ptrs, rank,
                        sg._epochs(1))

@@ -56,6 +56,7 @@ void gemm_bf16_ag(const void* const* a_bufs, const void* B, void* C, int M, int 
 // ---- attention.cu --------------------------------------------------------------------------
 // qkv: [B,S,nh+2*nkv,128] bf16 (q heads | k heads | v heads); o: [B,S,nh,128]; lse: [B,nh,S] fp32
 void attn_fwd(const void* qkv, void* o, float* lse, int B, int S, int nh, int nkv, float scale, cudaStream_t s);
+void attn_fwd2(const void* qkv, void* o, float* lse, int B, int S, int nh, int nkv, float scale, cudaStream_t s);
 void attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta, float* dq_acc,
               void* dqkv, int B, int S, int nh, int nkv, float scale, cudaStream_t s);
 

@@ -3,6 +3,8 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
+#include <cstdlib>
+
 #include "api.h"
 #include "comm_api.h"
 
@@ -17,14 +19,28 @@ void check_qkv(const Tensor& qkv, int64_t nh, int64_t nkv) {
               "qkv must be [B, S, nh+2*nkv, 128]");
 }
 
-std::tuple<Tensor, Tensor> py_attn_fwd(const Tensor& qkv, int64_t nh, int64_t nkv, double scale) {
+// version: 0 = default (DTG_ATTN_FWD env, else 2), 1 = one query tile per CTA (attention_fwd.cu),
+// 2 = two tiles per CTA, P kept in tensor memory (attention_fwd2.cu)
+int default_fwd_version() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DTG_ATTN_FWD");
+    v = e ? atoi(e) : 2;
+    if (v != 1 && v != 2) v = 2;
+  }
+  return v;
+}
+
+std::tuple<Tensor, Tensor> py_attn_fwd(const Tensor& qkv, int64_t nh, int64_t nkv, double scale, int64_t version) {
   check_qkv(qkv, nh, nkv);
   const c10::cuda::CUDAGuard guard(qkv.device());
   const int64_t B = qkv.size(0), S = qkv.size(1);
   Tensor o = torch::empty({B, S, nh, 128}, qkv.options());
   Tensor lse = torch::empty({B, nh, S}, qkv.options().dtype(at::kFloat));
-  dtg::attn_fwd(qkv.data_ptr(), o.data_ptr(), lse.data_ptr<float>(), (int)B, (int)S, (int)nh, (int)nkv, (float)scale,
-                at::cuda::getCurrentCUDAStream().stream());
+  if (version == 0) version = default_fwd_version();
+  auto fn = version == 1 ? dtg::attn_fwd : dtg::attn_fwd2;
+  fn(qkv.data_ptr(), o.data_ptr(), lse.data_ptr<float>(), (int)B, (int)S, (int)nh, (int)nkv, (float)scale,
+     at::cuda::getCurrentCUDAStream().stream());
   return {o, lse};
 }
 
@@ -49,7 +65,8 @@ Tensor py_attn_bwd(const Tensor& d_o, const Tensor& qkv, const Tensor& o, const 
 }  // namespace
 
 void bind_attention(pybind11::module_& m) {
-  m.def("attn_fwd", &py_attn_fwd);
+  m.def("attn_fwd", &py_attn_fwd, pybind11::arg("qkv"), pybind11::arg("nh"), pybind11::arg("nkv"), pybind11::arg("scale"),
+        pybind11::arg("version") = 0);
   m.def("attn_bwd", &py_attn_bwd, pybind11::arg("d_o"), pybind11::arg("qkv"), pybind11::arg("o"), pybind11::arg("lse"),
         pybind11::arg("nh"), pybind11::arg("nkv"), pybind11::arg("scale"), pybind11::arg("trace") = pybind11::none());
 }

@@ -375,7 +375,10 @@ class FSDPEngine:
                 if lazy:
                     # what the GEMMs do not fetch themselves: my own slice (a local copy) and the small tail
                     per = sh.padded_numel
-                    g.param[self.rank * per:(self.rank + 1) * per].copy_(sh.param, non_blocking=True)
+                    # (raw copies, not tensor ops: an in-place torch op on the slot would bump the autograd version
+                    # of every weight view another layer saved for its backward)
+                    self.symm.gather_range_(self._symm_of[sh.param.data_ptr()], g.param, self.rank * per,
+                                            (self.rank + 1) * per, per, barrier=False)
                     # the device barrier in front of the tail copies is also what orders every later read of the
                     # peers' shards (by the gather warps of this group's GEMMs, which wait for `ag_done`) behind
                     # the peers' previous optimizer work on their communication streams

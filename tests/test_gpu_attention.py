@@ -16,7 +16,31 @@ def _rel(a, b):
     return ((a - b).norm() / (b.norm() + 1e-12)).item(), (a - b).abs().max().item()
 
 
-@pytest.mark.parametrize("B,S,nh,nkv", [(1, 128, 1, 1), (2, 256, 4, 2), (1, 1024, 8, 2), (1, 512, 4, 4), (1, 2048, 2, 1)])
+@pytest.mark.parametrize("version", [1, 2])
+@pytest.mark.parametrize("B,S,nh,nkv", [(1, 128, 1, 1), (1, 256, 2, 1), (2, 384, 4, 2), (1, 1024, 8, 2), (1, 2048, 4, 4),
+                                        (1, 4096, 32, 4), (2, 640, 8, 1)])
+def test_attention_forward_versions(B, S, nh, nkv, version):
+    """Both forward kernels (1: one query tile per CTA; 2: two tiles per CTA, P in tensor memory) against fp32 —
+    including the bench shape (S 4096, 32 heads, GQA 8:1) and odd numbers of 128-row tiles (384, 640)."""
+    torch.manual_seed(0)
+    C = _ext.load(True)
+    d = 128
+    qkv = torch.randn(B, S, nh + 2 * nkv, d, device=DEV, dtype=torch.bfloat16)
+    o, lse = C.attn_fwd(qkv, nh, nkv, 1.0 / math.sqrt(d), version)
+    qf = qkv.float()
+    want = ref.attention(qf[:, :, :nh], qf[:, :, nh:nh + nkv], qf[:, :, nh + nkv:], causal=True)
+    rel, mx = _rel(o, want)
+    assert rel < 2e-2, f"forward v{version}: rel {rel:.4g} max {mx:.4g}"
+    q = qf[:, :, :nh].permute(0, 2, 1, 3)
+    k = qf[:, :, nh:nh + nkv].permute(0, 2, 1, 3).repeat_interleave(nh // nkv, 1)
+    if S <= 2048:
+        sc = (q @ k.transpose(-1, -2)) / math.sqrt(d)
+        sc = sc.masked_fill(~torch.ones(S, S, dtype=torch.bool, device=DEV).tril(), float("-inf"))
+        assert (lse - torch.logsumexp(sc, dim=-1)).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("B,S,nh,nkv", [(1, 128, 1, 1), (2, 256, 4, 2), (1, 1024, 8, 2), (1, 512, 4, 4), (1, 2048, 2, 1),
+                                        (1, 4096, 8, 1), (1, 384, 2, 2)])
 def test_attention_fwd_bwd(B, S, nh, nkv):
     torch.manual_seed(0)
     d = 128

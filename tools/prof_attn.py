@@ -11,6 +11,9 @@ qkv = torch.randn(B, S, nh + 2 * nkv, 128, device="cuda", dtype=torch.bfloat16)
 do = torch.randn(B, S, nh, 128, device="cuda", dtype=torch.bfloat16)
 sc = 1 / math.sqrt(128)
 o, lse = C.attn_fwd(qkv, nh, nkv, sc)
+for ver in (1, 2):
+    ms_v, _ = device_time_ms(lambda: C.attn_fwd(qkv, nh, nkv, sc, ver), warmup=2, iters=5)
+    print(f"attn fwd v{ver} {ms_v:.3f} ms = {4 * B * nh * S * S * 128 / 2 / ms_v / 1e9:.1f} TFLOP/s")
 ms_f, _ = device_time_ms(lambda: C.attn_fwd(qkv, nh, nkv, sc), warmup=2, iters=5)
 ms_b, _ = device_time_ms(lambda: C.attn_bwd(do, qkv, o, lse, nh, nkv, sc), warmup=2, iters=5)
 fl = 4 * B * nh * S * S * 128 / 2

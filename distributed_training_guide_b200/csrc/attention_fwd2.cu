@@ -16,6 +16,8 @@
 // Replaces torch SDPA / flash-attn-2 that the reference uses.
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "api.h"
 #include "attention_common.cuh"
 #include "common.cuh"
@@ -188,31 +190,37 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
       const uint32_t s_addr = lane_addr + TM_S + (uint32_t)t * 128;
       const uint32_t o_addr = lane_addr + TM_O + (uint32_t)t * 128;
       float m_use = -INFINITY, l_run = 0.f;   // m_use: the (possibly stale) row max every exponent is taken against
-      for (int j = 0; j < n_t; ++j) {
-        mbar_wait(&s_full[t], (uint32_t)(j & 1));
-        tc_fence_after();
-        const bool diag = (j == n_t - 1);
-        // ---- pass 1: row maximum ----
+      // one block of scores; DIAG (the last block of the tile) masks keys after the query
+      auto block = [&](auto diag_tag, int j) {
+        constexpr bool DIAG = decltype(diag_tag)::value;
+        // ---- pass 1: row maximum (two 64-column halves, both loads of a half in flight before the wait) ----
         float mx = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(s_addr + c * 32, r);
+        for (int h = 0; h < 2; ++h) {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32b_x32(s_addr + h * 64, r0);
+          tmem_ld_32x32b_x32(s_addr + h * 64 + 32, r1);
           tmem_ld_wait();
           float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            float v = __uint_as_float(r[i]);
-            if (diag && c * 32 + i > row) v = -INFINITY;
-            m4[i & 3] = fmaxf(m4[i & 3], v);
+            float a = __uint_as_float(r0[i]), b = __uint_as_float(r1[i]);
+            if (DIAG) {
+              if (h * 64 + i > row) a = -INFINITY;
+              if (h * 64 + 32 + i > row) b = -INFINITY;
+            }
+            m4[i & 3] = fmaxf(m4[i & 3], fmaxf(a, b));
           }
           mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
         }
-        // ---- lazy running max: rescale O (and l) only when the max moved by more than 2^RESCALE_LOG2 ----
-        if ((mx - m_use) * scale_log2 > RESCALE_LOG2) {      // always true on the first block (m_use = -inf)
-          const float alpha = fast_exp2((m_use - mx) * scale_log2);   // 0 on the first block
+        // ---- lazy running max: O (and l) are rescaled only when some row of the warp saw its max grow by more
+        //      than 2^RESCALE_LOG2.  The decision is WARP-UNIFORM: tcgen05.ld/st are .sync.aligned. ----
+        const bool moved = (mx - m_use) * scale_log2 > RESCALE_LOG2;      // always true on the first block
+        if (__any_sync(0xffffffffu, moved)) {
+          const float m_new = fmaxf(mx, m_use);
+          const float alpha = fast_exp2((m_use - m_new) * scale_log2);   // 0 on the first block (m_use = -inf)
           l_run *= alpha;
-          m_use = mx;
+          m_use = m_new;
           if (j > 0) {   // s_full(j) was committed after PV_t(j-1): O_t is quiescent
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -229,26 +237,38 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
         const float mb = m_use * scale_log2;
         float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(s_addr + c * 32, r);
+        for (int h = 0; h < 2; ++h) {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32b_x32(s_addr + h * 64, r0);
+          tmem_ld_32x32b_x32(s_addr + h * 64 + 32, r1);
           tmem_ld_wait();
-          uint32_t pk[16];
+          uint32_t pk[32];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            float p0 = fast_exp2(fmaf(__uint_as_float(r[i]), scale_log2, -mb));
-            float p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), scale_log2, -mb));
-            if (diag) {
-              if (c * 32 + i > row) p0 = 0.f;
-              if (c * 32 + i + 1 > row) p1 = 0.f;
+            float p0 = fast_exp2(fmaf(__uint_as_float(r0[i]), scale_log2, -mb));
+            float p1 = fast_exp2(fmaf(__uint_as_float(r0[i + 1]), scale_log2, -mb));
+            float p2 = fast_exp2(fmaf(__uint_as_float(r1[i]), scale_log2, -mb));
+            float p3 = fast_exp2(fmaf(__uint_as_float(r1[i + 1]), scale_log2, -mb));
+            if (DIAG) {
+              if (h * 64 + i > row) p0 = 0.f;
+              if (h * 64 + i + 1 > row) p1 = 0.f;
+              if (h * 64 + 32 + i > row) p2 = 0.f;
+              if (h * 64 + 32 + i + 1 > row) p3 = 0.f;
             }
-            sum4[(i >> 1) & 3] += p0 + p1;
-            __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
-            pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+            sum4[(i >> 1) & 3] += (p0 + p1) + (p2 + p3);
+            __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1), hi = __floats2bfloat162_rn(p2, p3);
+            pk[i >> 1] = *reinterpret_cast<uint32_t*>(&lo);
+            pk[16 + (i >> 1)] = *reinterpret_cast<uint32_t*>(&hi);
           }
-          tmem_st_32x32b_x16(s_addr + c * 16, pk);   // columns [16c, 16c+16) lie inside the chunks already read
+          tmem_st_32x32b_x32(s_addr + h * 32, pk);   // P columns [32h, 32h+32) lie inside the score columns already read
         }
         l_run += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      };
+      for (int j = 0; j < n_t; ++j) {
+        mbar_wait(&s_full[t], (uint32_t)(j & 1));
+        tc_fence_after();
+        if (j == n_t - 1) block(std::true_type{}, j);
+        else block(std::false_type{}, j);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();

@@ -39,6 +39,30 @@ def test_attention_forward_versions(B, S, nh, nkv, version):
         assert (lse - torch.logsumexp(sc, dim=-1)).abs().max().item() < 2e-2
 
 
+@pytest.mark.parametrize("version", [1, 2])
+def test_attention_forward_row_max_jumps_late(version):
+    """Scores whose row maximum grows by far more than the lazy-rescale threshold in LATE key blocks, for SOME rows of
+    a warp only (v2 rescales O in tensor memory with warp-collective tcgen05.ld/st: the decision must be warp-uniform;
+    random-normal inputs never take that branch after the first block)."""
+    torch.manual_seed(3)
+    C = _ext.load(True)
+    B, S, nh, nkv, d = 1, 1024, 4, 2, 128
+    qkv = torch.randn(B, S, nh + 2 * nkv, d, device=DEV, dtype=torch.bfloat16)
+    boost = torch.ones(S, device=DEV)
+    boost[300:310] = 5.0
+    boost[700:] = 9.0                         # late keys dominate
+    rows = torch.ones(S, device=DEV)
+    rows[::3] = 0.05                          # every third query barely reacts: its max does not move
+    qkv[:, :, nh:nh + nkv] *= boost[None, :, None, None].to(qkv.dtype)
+    qkv[:, :, :nh] *= rows[None, :, None, None].to(qkv.dtype)
+    o, lse = C.attn_fwd(qkv, nh, nkv, 1.0 / math.sqrt(d), version)
+    torch.cuda.synchronize()
+    qf = qkv.float()
+    want = ref.attention(qf[:, :, :nh], qf[:, :, nh:nh + nkv], qf[:, :, nh + nkv:], causal=True)
+    rel, mx = _rel(o, want)
+    assert rel < 2e-2, f"forward v{version}: rel {rel:.4g} max {mx:.4g}"
+
+
 @pytest.mark.parametrize("B,S,nh,nkv", [(1, 128, 1, 1), (2, 256, 4, 2), (1, 1024, 8, 2), (1, 512, 4, 4), (1, 2048, 2, 1),
                                         (1, 4096, 8, 1), (1, 384, 2, 2)])
 def test_attention_fwd_bwd(B, S, nh, nkv):

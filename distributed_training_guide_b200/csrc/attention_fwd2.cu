@@ -264,11 +264,47 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
         }
         l_run += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
       };
+      // Interior blocks, common case in ONE pass over the scores: exponentiate against the current (stale) max while
+      // tracking the true row max; only if some row of the warp outgrew the threshold is the block redone exactly
+      // (the scores are still intact: P is kept in registers until the check).  Returns false if it must be redone.
+      auto fast_block = [&]() -> bool {
+        const float mb = m_use * scale_log2;
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t pk[64];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32b_x32(s_addr + h * 64, r0);
+          tmem_ld_32x32b_x32(s_addr + h * 64 + 32, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float a0 = __uint_as_float(r0[i]), a1 = __uint_as_float(r0[i + 1]);
+            const float b0 = __uint_as_float(r1[i]), b1 = __uint_as_float(r1[i + 1]);
+            mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(fmaxf(a0, a1), fmaxf(b0, b1)));
+            const float p0 = fast_exp2(fmaf(a0, scale_log2, -mb)), p1 = fast_exp2(fmaf(a1, scale_log2, -mb));
+            const float p2 = fast_exp2(fmaf(b0, scale_log2, -mb)), p3 = fast_exp2(fmaf(b1, scale_log2, -mb));
+            sum4[(i >> 1) & 3] += (p0 + p1) + (p2 + p3);
+            __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1), hi = __floats2bfloat162_rn(p2, p3);
+            pk[h * 32 + (i >> 1)] = *reinterpret_cast<uint32_t*>(&lo);
+            pk[h * 32 + 16 + (i >> 1)] = *reinterpret_cast<uint32_t*>(&hi);
+          }
+        }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        if (__any_sync(0xffffffffu, (mx - m_use) * scale_log2 > RESCALE_LOG2)) return false;
+        uint32_t(&lo32)[32] = *reinterpret_cast<uint32_t(*)[32]>(&pk[0]);
+        uint32_t(&hi32)[32] = *reinterpret_cast<uint32_t(*)[32]>(&pk[32]);
+        tmem_st_32x32b_x32(s_addr, lo32);
+        tmem_st_32x32b_x32(s_addr + 32, hi32);
+        l_run += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+        return true;
+      };
       for (int j = 0; j < n_t; ++j) {
         mbar_wait(&s_full[t], (uint32_t)(j & 1));
         tc_fence_after();
         if (j == n_t - 1) block(std::true_type{}, j);
-        else block(std::false_type{}, j);
+        else if (j == 0 || !fast_block()) block(std::false_type{}, j);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();

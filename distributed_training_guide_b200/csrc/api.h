@@ -20,6 +20,8 @@ void swiglu_fwd(const void* gu, void* h, long long T, int I, cudaStream_t s);
 void swiglu_bwd(const void* dh, const void* gu, void* dgu, long long T, int I, cudaStream_t s);
 void embedding_fwd(const long long* ids, const void* w, void* out, long long T, int H, cudaStream_t s);
 void embedding_bwd(const void* dout, const long long* ids, void* dw, long long T, int H, cudaStream_t s);
+void embedding_bwd_sorted(const void* dout, const long long* ids_sorted, const long long* perm, void* dw, long long T, int H,
+                          bool accumulate, cudaStream_t s);
 void scale_inplace(void* x, const float* scale, long long n, cudaStream_t s);
 
 // ---- cross_entropy.cu ----------------------------------------------------------------------

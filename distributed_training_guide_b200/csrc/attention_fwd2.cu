@@ -248,7 +248,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
             float p0 = fast_exp2(fmaf(__uint_as_float(r0[i]), scale_log2, -mb));
             float p1 = fast_exp2(fmaf(__uint_as_float(r0[i + 1]), scale_log2, -mb));
             float p2 = fast_exp2(fmaf(__uint_as_float(r1[i]), scale_log2, -mb));
-            float p3 = fast_exp2(fmaf(__uint_as_float(r1[i + 1]), scale_log2, -mb));
+            float p3 = poly_exp2(fmaf(__uint_as_float(r1[i + 1]), scale_log2, -mb));
             if (DIAG) {
               if (h * 64 + i > row) p0 = 0.f;
               if (h * 64 + i + 1 > row) p1 = 0.f;
@@ -284,7 +284,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
             const float b0 = __uint_as_float(r1[i]), b1 = __uint_as_float(r1[i + 1]);
             mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(fmaxf(a0, a1), fmaxf(b0, b1)));
             const float p0 = fast_exp2(fmaf(a0, scale_log2, -mb)), p1 = fast_exp2(fmaf(a1, scale_log2, -mb));
-            const float p2 = fast_exp2(fmaf(b0, scale_log2, -mb)), p3 = fast_exp2(fmaf(b1, scale_log2, -mb));
+            // one exponential in four on the FMA pipes (poly_exp2): the SFU alone would be as busy as the tensor core
+            const float p2 = fast_exp2(fmaf(b0, scale_log2, -mb)), p3 = poly_exp2(fmaf(b1, scale_log2, -mb));
             sum4[(i >> 1) & 3] += (p0 + p1) + (p2 + p3);
             __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1), hi = __floats2bfloat162_rn(p2, p3);
             pk[h * 32 + (i >> 1)] = *reinterpret_cast<uint32_t*>(&lo);

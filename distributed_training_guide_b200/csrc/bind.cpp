@@ -139,6 +139,17 @@ Tensor embedding_fwd(const Tensor& ids, const Tensor& w) {
                      (int)w.size(1), stream());
   return out;
 }
+void embedding_bwd_sorted(const Tensor& dout, const Tensor& ids_sorted, const Tensor& perm, Tensor& dw, bool accumulate) {
+  TORCH_CHECK(dout.is_contiguous() && dw.is_contiguous() && ids_sorted.is_contiguous() && perm.is_contiguous(), "contiguous");
+  TORCH_CHECK(dout.scalar_type() == at::kBFloat16 && dw.scalar_type() == at::kBFloat16, "bf16 gradients");
+  TORCH_CHECK(ids_sorted.scalar_type() == at::kLong && perm.scalar_type() == at::kLong && perm.numel() == ids_sorted.numel(),
+              "int64 ids / permutation");
+  const c10::cuda::CUDAGuard guard(dw.device());
+  dtg::embedding_bwd_sorted(dout.data_ptr(), (const long long*)ids_sorted.data_ptr<int64_t>(),
+                            (const long long*)perm.data_ptr<int64_t>(), dw.data_ptr(), ids_sorted.numel(),
+                            (int)dw.size(1), accumulate, at::cuda::getCurrentCUDAStream().stream());
+}
+
 void embedding_bwd(const Tensor& dout, const Tensor& ids, Tensor& dw) {
   check_contig(dout, "dout", at::kBFloat16);
   check_contig(ids, "ids", at::kLong);
@@ -178,6 +189,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("scale_inplace", &scale_inplace);
   m.def("embedding_fwd", &embedding_fwd);
   m.def("embedding_bwd", &embedding_bwd);
+  m.def("embedding_bwd_sorted", &embedding_bwd_sorted);
   m.def("adamw_flat", &adamw_flat);
   dtg::bind_comm(m);
   dtg::bind_attention(m);

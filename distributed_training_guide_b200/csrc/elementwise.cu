@@ -358,6 +358,39 @@ __global__ void embedding_bwd_kernel(const __nv_bfloat16* __restrict__ dout, con
   }
 }
 
+// Deterministic variant (--deterministic): the caller passes the token ids stably sorted with the permutation that
+// sorted them; the CTA that starts a run of equal ids sums that run's gradient rows in ascending token order in
+// fp32 and writes (or accumulates into) the one table row — no atomics, bit-identical from run to run.
+__global__ void embedding_bwd_sorted_kernel(const __nv_bfloat16* __restrict__ dout, const long long* __restrict__ ids_sorted,
+                                            const long long* __restrict__ perm, __nv_bfloat16* __restrict__ dw,
+                                            long long T, int H, int accumulate) {
+  const long long p0 = blockIdx.x;
+  const long long id = ids_sorted[p0];
+  if (p0 > 0 && ids_sorted[p0 - 1] == id) return;   // not the start of a run
+  for (int c = threadIdx.x; c < (H >> 3); c += blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (accumulate) unpack8(ld8(dw + id * H + c * 8), acc);
+    for (long long p = p0; p < T && ids_sorted[p] == id; ++p) {
+      float g[8];
+      unpack8(ld8(dout + perm[p] * H + c * 8), g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += g[j];
+    }
+    st8(dw + id * H + c * 8, pack8(acc));
+  }
+}
+void embedding_bwd_sorted(const void* dout, const long long* ids_sorted, const long long* perm, void* dw, long long T, int H,
+                          bool accumulate, cudaStream_t s) {
+  if (H % 8 != 0) throw std::runtime_error("embedding: hidden size must be a multiple of 8");
+  if (T <= 0) return;
+  embedding_bwd_sorted_kernel<<<(unsigned)T, 128, 0, s>>>((const __nv_bfloat16*)dout, ids_sorted, perm, (__nv_bfloat16*)dw, T, H,
+                                                       accumulate ? 1 : 0);
+  note_launch();
+  DTG_LAUNCH_CHECK();
+}
+
 void embedding_fwd(const long long* ids, const void* w, void* out, long long T, int H, cudaStream_t s) {
   if (H % 8 != 0) throw std::runtime_error("embedding: hidden size must be a multiple of 8");
   embedding_fwd_kernel<<<ew_grid(T * (H / 8)), 256, 0, s>>>(ids, (const __nv_bfloat16*)w, (__nv_bfloat16*)out, T, H);

@@ -124,6 +124,22 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// 2^x WITHOUT the SFU: B200 evaluates MUFU.EX2 at 16 results / clock / SM, the same time a 128x128x128 attention
+// block needs on the tensor core — softmax warps that send every exponential through it leave no slack for the two
+// pipes to overlap.  Cody-Waite split (floor via a round-down add of 1.5*2^23, so the integer part sits in the low
+// mantissa bits) + a degree-3 minimax polynomial for 2^f on [0, 1) (max rel. error ~1e-4, far below bf16's 2^-8) +
+// an integer add into the exponent field: 9 FMA/ALU-pipe instructions, no SFU.  x is clamped to >= -126.
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -126.f);
+  float t;
+  asm("add.rm.ftz.f32 %0, %1, %2;" : "=f"(t) : "f"(x), "f"(12582912.f));
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(0.077119089663028717f, f, 0.227564394474029541f);
+  p = fmaf(p, f, 0.695146143436431885f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 // ---- TMA -----------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

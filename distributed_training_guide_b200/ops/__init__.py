@@ -389,9 +389,17 @@ class _Embedding(torch.autograd.Function):
         d2 = dout.reshape(-1, dout.shape[-1]).contiguous()
 
         def into(out, acc):
+            flat = ids.reshape(-1)
+            if torch.are_deterministic_algorithms_enabled():
+                # --deterministic: sorted runs summed in token order, no atomics (bit-identical run to run)
+                if not acc:
+                    out.zero_()
+                srt, perm = torch.sort(flat, stable=True)
+                C.embedding_bwd_sorted(d2, srt.contiguous(), perm.contiguous(), out, True)
+                return
             if not acc:
                 out.zero_()
-            C.embedding_bwd(d2, ids.reshape(-1), out)
+            C.embedding_bwd(d2, flat, out)
 
         return None, _emit_weight_grad(w, into, w)
 

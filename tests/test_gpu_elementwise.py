@@ -142,3 +142,30 @@ def test_adamw_flat(n, state_dtype):
             pr.data = pr.data.to(torch.bfloat16).float()  # parameters are stored in bf16 each step
     tol = 2e-2 if state_dtype == torch.float32 else 6e-2
     _close(p, pr.data, tol, 2e-2, "adamw")
+
+
+def test_embedding_backward_deterministic_mode():
+    """--deterministic routes the embedding gradient through the sorted, atomics-free kernel: equal to the fp32
+    reference and bit-identical across runs (heavily repeated ids make the atomic version order-dependent)."""
+    from distributed_training_guide_b200 import ops
+
+    torch.manual_seed(0)
+    V, H, T = 512, 1024, 8192
+    w = (torch.randn(V, H, device="cuda") * 0.02).to(torch.bfloat16).requires_grad_(True)
+    ids = torch.randint(0, 16, (2, T // 2), device="cuda")     # 16 distinct ids: ~512 rows summed per table row
+    dout = torch.randn(2, T // 2, H, device="cuda").to(torch.bfloat16)
+    want = torch.zeros(V, H, device="cuda")
+    want.index_add_(0, ids.reshape(-1), dout.reshape(-1, H).float())
+    outs = []
+    prev = torch.are_deterministic_algorithms_enabled()
+    torch.use_deterministic_algorithms(True, warn_only=True)
+    try:
+        for _ in range(3):
+            w.grad = None
+            ops.embedding(ids, w).backward(dout)
+            outs.append(w.grad.clone())
+    finally:
+        torch.use_deterministic_algorithms(prev, warn_only=True)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    err = (outs[0].float() - want).abs().max().item() / want.abs().max().item()
+    assert err < 1e-2, err

@@ -32,8 +32,13 @@ def summarize(rep):
     hdr, units = rows[0], rows[1]
     name = os.path.splitext(os.path.basename(rep))[0]
     md = [f"# ncu summary: {name}", "", f"source: `{rep}` (captured with `ncu --set full --clock-control none --import-source on`)", ""]
+    seen = set()
     for r in rows[2:]:
         d = dict(zip(hdr, r))
+        key = (d.get("Kernel Name", "?"), d.get("launch__grid_size", ""))
+        if key in seen:        # a step capture launches the same kernel many times: keep the first of each (name, grid)
+            continue
+        seen.add(key)
         md.append(f"## {d.get('Kernel Name', '?')[:150]}")
         md.append("")
         md.append("| metric | value | unit |")

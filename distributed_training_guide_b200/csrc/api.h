@@ -60,6 +60,6 @@ void gemm_bf16_ag(const void* const* a_bufs, const void* B, void* C, int M, int 
 void attn_fwd(const void* qkv, void* o, float* lse, int B, int S, int nh, int nkv, float scale, cudaStream_t s);
 void attn_fwd2(const void* qkv, void* o, float* lse, int B, int S, int nh, int nkv, float scale, cudaStream_t s);
 void attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta, float* dq_acc,
-              void* dqkv, int B, int S, int nh, int nkv, float scale, cudaStream_t s);
+              void* dqkv, int B, int S, int nh, int nkv, float scale, int mode, cudaStream_t s);
 
 }  // namespace dtg

@@ -45,7 +45,7 @@ std::tuple<Tensor, Tensor> py_attn_fwd(const Tensor& qkv, int64_t nh, int64_t nk
 }
 
 Tensor py_attn_bwd(const Tensor& d_o, const Tensor& qkv, const Tensor& o, const Tensor& lse, int64_t nh, int64_t nkv,
-                   double scale, const c10::optional<Tensor>& trace) {
+                   double scale, const c10::optional<Tensor>& trace, int64_t mode) {
   check_qkv(qkv, nh, nkv);
   TORCH_CHECK(d_o.is_contiguous() && o.is_contiguous() && d_o.scalar_type() == at::kBFloat16, "dO/O must be contiguous bf16");
   const c10::cuda::CUDAGuard guard(qkv.device());
@@ -58,7 +58,7 @@ Tensor py_attn_bwd(const Tensor& d_o, const Tensor& qkv, const Tensor& o, const 
     tr = reinterpret_cast<float*>(trace->data_ptr<int64_t>());
   }
   dtg::attn_bwd(qkv.data_ptr(), o.data_ptr(), d_o.data_ptr(), lse.data_ptr<float>(), delta.data_ptr<float>(), tr,
-                dqkv.data_ptr(), (int)B, (int)S, (int)nh, (int)nkv, (float)scale,
+                dqkv.data_ptr(), (int)B, (int)S, (int)nh, (int)nkv, (float)scale, (int)mode,
                 at::cuda::getCurrentCUDAStream().stream());
   return dqkv;
 }
@@ -68,6 +68,7 @@ void bind_attention(pybind11::module_& m) {
   m.def("attn_fwd", &py_attn_fwd, pybind11::arg("qkv"), pybind11::arg("nh"), pybind11::arg("nkv"), pybind11::arg("scale"),
         pybind11::arg("version") = 0);
   m.def("attn_bwd", &py_attn_bwd, pybind11::arg("d_o"), pybind11::arg("qkv"), pybind11::arg("o"), pybind11::arg("lse"),
-        pybind11::arg("nh"), pybind11::arg("nkv"), pybind11::arg("scale"), pybind11::arg("trace") = pybind11::none());
+        pybind11::arg("nh"), pybind11::arg("nkv"), pybind11::arg("scale"), pybind11::arg("trace") = pybind11::none(),
+        pybind11::arg("mode") = 0);   // 0 = default (DTG_ATTN_BWD), 1 = P/dS through shared memory, 2 = P/dS in TMEM
 }
 }  // namespace dtg

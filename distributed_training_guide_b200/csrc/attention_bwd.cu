@@ -18,6 +18,8 @@
 // qkv dgrad/wgrad GEMMs consume it directly.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "api.h"
 #include "attention_common.cuh"
 #include "common.cuh"
@@ -70,7 +72,11 @@ __global__ void attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ d_o, con
   }
 }
 
-template <bool KV_MODE>
+// TS = true: P^T / dS^T (KV pass) and dS (Q pass) never go through shared memory — the softmax threads write them as
+// packed bf16 over the S / dP scores they were computed from (tcgen05.st) and the gradient MMAs read their A operand
+// from tensor memory (TS form).  Per 128x64 block that removes 32 KB of shared-memory stores and 32 KB of A-operand
+// reads out of ~192 KB: the N=64 MMAs of this kernel are shared-memory-bandwidth-bound (profiles/prof_attn_bwd.md).
+template <bool KV_MODE, bool TS>
 __global__ void __launch_bounds__(bwd::THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_constant__ CUtensorMap tm_qkv_c,
                 const __grid_constant__ CUtensorMap tm_do_r, const __grid_constant__ CUtensorMap tm_do_c,
@@ -186,7 +192,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
         const uint32_t ph = (uint32_t)((t >> 1) & 1);
         const int ys = t % Y_STAGES;                // shared-memory stage of the streamed tiles
         mbar_wait(&y_full[ys], (uint32_t)((t / Y_STAGES) & 1));
-        mbar_wait(&sdp_empty[st], ph ^ 1);
+        // TS: buffer st is free once the gradient MMAs of block t-2 (which read P / dS from it) have been issued —
+        // they were, in this thread's program order, and tcgen05.mma executes in issue order
+        if (!TS) mbar_wait(&sdp_empty[st], ph ^ 1);
         tc_fence_after();
         const uint32_t y1 = smem_u32(smem + OFF_Y + ys * 2 * C_TILE), y2 = y1 + C_TILE;
 #pragma unroll
@@ -215,16 +223,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
         if (tracing && t < 64) trace[t * 8 + 5] = clock64();
         tc_fence_after();
         const uint32_t y1 = smem_u32(smem + OFF_Y + ys * 2 * C_TILE), y2 = y1 + C_TILE;
+        const uint32_t st_g = (uint32_t)(t & 1);
         if (KV_MODE) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)  // dV += P^T dO_C
-            mma_f16_ss<1>(tmem_base + TM_ACC_A, desc_kmajor_sw128(sp + kk * 32),
-                          desc_mnmajor_sw128(y2 + kk * 2048, C_HALF), idesc_g, (t | kk) ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk) {  // dV += P^T dO_C
+            if (TS)
+              mma_f16_ts(tmem_base + TM_ACC_A, tmem_base + TM_S + st_g * 64 + kk * 8,
+                         desc_mnmajor_sw128(y2 + kk * 2048, C_HALF), idesc_g, (t | kk) ? 1u : 0u);
+            else
+              mma_f16_ss<1>(tmem_base + TM_ACC_A, desc_kmajor_sw128(sp + kk * 32),
+                            desc_mnmajor_sw128(y2 + kk * 2048, C_HALF), idesc_g, (t | kk) ? 1u : 0u);
+          }
         }
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)  // dK += dS^T Q_C   /   dQ += dS K_C
-          mma_f16_ss<1>(tmem_base + TM_ACC_B, desc_kmajor_sw128(sds + kk * 32),
-                        desc_mnmajor_sw128(y1 + kk * 2048, C_HALF), idesc_g, (t | kk) ? 1u : 0u);
+        for (int kk = 0; kk < 4; ++kk) {  // dK += dS^T Q_C   /   dQ += dS K_C
+          if (TS)
+            mma_f16_ts(tmem_base + TM_ACC_B, tmem_base + TM_DP + st_g * 64 + kk * 8,
+                       desc_mnmajor_sw128(y1 + kk * 2048, C_HALF), idesc_g, (t | kk) ? 1u : 0u);
+          else
+            mma_f16_ss<1>(tmem_base + TM_ACC_B, desc_kmajor_sw128(sds + kk * 32),
+                          desc_mnmajor_sw128(y1 + kk * 2048, C_HALF), idesc_g, (t | kk) ? 1u : 0u);
+        }
         mma_commit(pds_empty);
         mma_commit(&y_empty[ys]);
         if (tracing && t < 64) trace[t * 8 + 6] = clock64();
@@ -269,9 +288,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       tmem_ld_32x32b_x32(lane_addr + TM_S + st * 64 + half * 32, rs);
       tmem_ld_32x32b_x32(lane_addr + TM_DP + st * 64 + half * 32, rd);
       tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sdp_empty[st]);
+      if (!TS) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sdp_empty[st]);
+      }
       // causal: query index >= key index.  Only blocks that touch the diagonal need the compare.
       const bool need_mask = KV_MODE ? (C0 < R0 + 127) : (C0 + 31 > R0);
       uint32_t pk_p[16], pk_ds[16];  // 32 bf16 each
@@ -296,17 +317,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
         pk_ds[i >> 1] = *reinterpret_cast<uint32_t*>(&b);
       }
       if (tr) trace[t * 8 + 1] = clock64();
-      if (t > 0) mbar_wait(pds_empty, (uint32_t)((t - 1) & 1));  // gradient MMAs of t-1 released P / dS
-      if (tr) trace[t * 8 + 2] = clock64();
+      if (TS) {
+        // over the scores just read: P^T -> S buffer, dS -> dP buffer of this stage, my 16 packed columns each.
+        // (The other half-row thread may still be loading ITS 32 score columns: disjoint from the 16 packed columns
+        // [16*half, 16*half+16) only for half 0; so both threads of a row sync on the named barrier first.)
+        named_bar_sync(1 + q, 64);
+        if (KV_MODE) tmem_st_32x32b_x16(lane_addr + TM_S + st * 64 + half * 16, pk_p);
+        tmem_st_32x32b_x16(lane_addr + TM_DP + st * 64 + half * 16, pk_ds);
+        tmem_st_wait();
+      } else {
+        if (t > 0) mbar_wait(pds_empty, (uint32_t)((t - 1) & 1));  // gradient MMAs of t-1 released P / dS
+        if (tr) trace[t * 8 + 2] = clock64();
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {  // my 4 chunks of 8 bf16 inside the 64-wide row, 128B swizzle
-        const uint32_t off = (uint32_t)((((half * 4 + ch) ^ (r & 7))) << 4);
-        if (KV_MODE)
-          *reinterpret_cast<uint4*>(sp + off) = make_uint4(pk_p[ch * 4], pk_p[ch * 4 + 1], pk_p[ch * 4 + 2], pk_p[ch * 4 + 3]);
-        *reinterpret_cast<uint4*>(sds + off) =
-            make_uint4(pk_ds[ch * 4], pk_ds[ch * 4 + 1], pk_ds[ch * 4 + 2], pk_ds[ch * 4 + 3]);
+        for (int ch = 0; ch < 4; ++ch) {  // my 4 chunks of 8 bf16 inside the 64-wide row, 128B swizzle
+          const uint32_t off = (uint32_t)((((half * 4 + ch) ^ (r & 7))) << 4);
+          if (KV_MODE)
+            *reinterpret_cast<uint4*>(sp + off) = make_uint4(pk_p[ch * 4], pk_p[ch * 4 + 1], pk_p[ch * 4 + 2], pk_p[ch * 4 + 3]);
+          *reinterpret_cast<uint4*>(sds + off) =
+              make_uint4(pk_ds[ch * 4], pk_ds[ch * 4 + 1], pk_ds[ch * 4 + 2], pk_ds[ch * 4 + 3]);
+        }
+        fence_proxy_async();
       }
-      fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
@@ -346,7 +377,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
 }
 
 void attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta, float* trace_buf,
-              void* dqkv, int B, int S, int nh, int nkv, float scale, cudaStream_t s) {
+              void* dqkv, int B, int S, int nh, int nkv, float scale, int mode, cudaStream_t s) {
   long long* trace = reinterpret_cast<long long*>(trace_buf);  // [2][64][8] int64 or nullptr
   if (S % 128 != 0) throw std::runtime_error("attn_bwd: sequence length must be a multiple of 128");
   const long long rows = (long long)B * S * nh;
@@ -358,15 +389,29 @@ void attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse,
   const CUtensorMap td_c = make_tmap_heads(d_o, B, S, nh, 64);
   static bool attr = false;
   if (!attr) {
-    DTG_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SMEM_BYTES));
-    DTG_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SMEM_BYTES));
+    DTG_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SMEM_BYTES));
+    DTG_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SMEM_BYTES));
+    DTG_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SMEM_BYTES));
+    DTG_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SMEM_BYTES));
     attr = true;
   }
+  static const bool ts_default = []() {   // DTG_ATTN_BWD=ts|ss
+    const char* e = getenv("DTG_ATTN_BWD");
+    return e ? e[0] == 't' : false;
+  }();
+  const bool ts = mode == 0 ? ts_default : mode == 2;   // mode: 0 default, 1 = ss, 2 = ts
   const int nblk = S / 128;
-  attn_bwd_kernel<true><<<dim3(B * nkv, nblk, 1), bwd::THREADS, bwd::SMEM_BYTES, s>>>(
-      tq_r, tq_c, td_r, td_c, lse, delta, (__nv_bfloat16*)dqkv, S, nh, nkv, scale, nblk, trace);
-  attn_bwd_kernel<false><<<dim3(B * nh, nblk, 1), bwd::THREADS, bwd::SMEM_BYTES, s>>>(
-      tq_r, tq_c, td_r, td_c, lse, delta, (__nv_bfloat16*)dqkv, S, nh, nkv, scale, nblk, trace ? trace + 512 : nullptr);
+  if (ts) {
+    attn_bwd_kernel<true, true><<<dim3(B * nkv, nblk, 1), bwd::THREADS, bwd::SMEM_BYTES, s>>>(
+        tq_r, tq_c, td_r, td_c, lse, delta, (__nv_bfloat16*)dqkv, S, nh, nkv, scale, nblk, trace);
+    attn_bwd_kernel<false, true><<<dim3(B * nh, nblk, 1), bwd::THREADS, bwd::SMEM_BYTES, s>>>(
+        tq_r, tq_c, td_r, td_c, lse, delta, (__nv_bfloat16*)dqkv, S, nh, nkv, scale, nblk, trace ? trace + 512 : nullptr);
+  } else {
+    attn_bwd_kernel<true, false><<<dim3(B * nkv, nblk, 1), bwd::THREADS, bwd::SMEM_BYTES, s>>>(
+        tq_r, tq_c, td_r, td_c, lse, delta, (__nv_bfloat16*)dqkv, S, nh, nkv, scale, nblk, trace);
+    attn_bwd_kernel<false, false><<<dim3(B * nh, nblk, 1), bwd::THREADS, bwd::SMEM_BYTES, s>>>(
+        tq_r, tq_c, td_r, td_c, lse, delta, (__nv_bfloat16*)dqkv, S, nh, nkv, scale, nblk, trace ? trace + 512 : nullptr);
+  }
   note_launch(3);
   DTG_LAUNCH_CHECK();
 }

@@ -83,6 +83,27 @@ def test_attention_fwd_bwd(B, S, nh, nkv):
         assert rel < 3e-2, f"{name}: rel {rel:.4g} max {mx:.4g}"
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("B,S,nh,nkv", [(1, 256, 2, 1), (1, 1024, 8, 2), (1, 2048, 4, 4), (2, 384, 4, 2)])
+def test_attention_backward_modes(B, S, nh, nkv, mode):
+    """Backward with P / dS staged through shared memory (mode 1) and kept in tensor memory (mode 2, TS-form gradient
+    MMAs) against the fp32 reference."""
+    torch.manual_seed(0)
+    C = _ext.load(True)
+    d = 128
+    sc = 1.0 / math.sqrt(d)
+    qkv = torch.randn(B, S, nh + 2 * nkv, d, device=DEV, dtype=torch.bfloat16)
+    do = torch.randn(B, S, nh, d, device=DEV, dtype=torch.bfloat16)
+    o, lse = C.attn_fwd(qkv, nh, nkv, sc, 1)
+    g = C.attn_bwd(do, qkv, o, lse, nh, nkv, sc, None, mode)
+    qf = qkv.float().requires_grad_(True)
+    want = ref.attention(qf[:, :, :nh], qf[:, :, nh:nh + nkv], qf[:, :, nh + nkv:], causal=True)
+    want.backward(do.float())
+    for name, sl in (("dq", slice(0, nh)), ("dk", slice(nh, nh + nkv)), ("dv", slice(nh + nkv, nh + 2 * nkv))):
+        rel, mx = _rel(g[:, :, sl], qf.grad[:, :, sl])
+        assert rel < 3e-2, f"mode {mode} {name}: rel {rel:.4g} max {mx:.4g}"
+
+
 def test_attention_lse():
     torch.manual_seed(1)
     C = _ext.load(True)

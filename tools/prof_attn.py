@@ -15,6 +15,10 @@ for ver in (1, 2):
     ms_v, _ = device_time_ms(lambda: C.attn_fwd(qkv, nh, nkv, sc, ver), warmup=2, iters=5)
     print(f"attn fwd v{ver} {ms_v:.3f} ms = {4 * B * nh * S * S * 128 / 2 / ms_v / 1e9:.1f} TFLOP/s")
 ms_f, _ = device_time_ms(lambda: C.attn_fwd(qkv, nh, nkv, sc), warmup=2, iters=5)
+for mode in (1, 2):
+    ms_m, _ = device_time_ms(lambda: C.attn_bwd(do, qkv, o, lse, nh, nkv, sc, None, mode), warmup=2, iters=5)
+    print(f"attn bwd mode {mode} ({'P/dS via smem' if mode == 1 else 'P/dS in TMEM'}) {ms_m:.3f} ms = "
+          f"{2.5 * 4 * B * nh * S * S * 128 / 2 / ms_m / 1e9:.1f} TFLOP/s (5-GEMM count)")
 ms_b, _ = device_time_ms(lambda: C.attn_bwd(do, qkv, o, lse, nh, nkv, sc), warmup=2, iters=5)
 fl = 4 * B * nh * S * S * 128 / 2
 print(f"attn fwd {ms_f:.3f} ms = {fl / ms_f / 1e9:.1f} TFLOP/s ; bwd {ms_b:.3f} ms = {2.5 * fl / ms_b / 1e9:.1f} TFLOP/s (5-GEMM count)")

@@ -259,7 +259,7 @@ def run_b200(args):
     h2d_bytes = sum(v.numel() * v.element_size() for v in host_batches[0].values())
 
     eng.phase_timing = bool(os.environ.get("DTG_PHASE_TIMING"))
-    ddp_engine = getattr(eng.model, "engine", None)
+    ddp_engine = getattr(eng.model, "engine", None) or getattr(eng.strategy, "engine", None)
     if world > 1 and hasattr(ddp_engine, "measure_tail"):
         ddp_engine.measure_tail = True   # two CUDA events per step: exposed communication = comm stream past backward
     _stage(f"engine ready; {args.warmup} warm-up steps", budget_s=BUDGET["warmup"] + 2 * args.warmup)
@@ -306,6 +306,8 @@ def run_b200(args):
         _barrier_sync(dev)
     launches = _ext.launch_count() - l0
     ms_dev = _dist_max(s.elapsed_time(e), dev) / args.steps
+    _stage(f"device-timed region: {ms_dev:.2f} ms/step = {1000.0 * eng.tokens_per_step / ms_dev:.0f} tokens/s "
+           f"(interim; the JSON line follows the end-to-end region)")
     # ---- region 2: end to end through the public API: pinned H2D every step + loss D2H every step ---
     _stage(f"timing {args.steps} steps end to end (pinned H2D + loss D2H every step)", budget_s=BUDGET["e2e"] + 2 * args.steps)
     eng.step(host_batches[args.steps])

@@ -112,9 +112,12 @@ class FSDPEngine:
         # Unshard fused into the consuming GEMMs (csrc/gemm_tcgen05.cu, B_MODE 3): the big matrices of a group are
         # gathered by the GEMM kernel that reads them; only the small tail (norm gains) keeps a prefetched copy.
         # Needs every matrix to start and end on a chunk boundary of the flat layout and every shard to be a whole
-        # number of chunks; DTG_FSDP_GATHER=ce keeps round 1's copy-engine unshard of whole groups.
+        # number of chunks.  Selected with DTG_FSDP_GATHER=gemm; the DEFAULT is the copy-engine unshard of whole groups
+        # ("ce"), which measured faster on 8xB200 (Llama-2-7B: 189.2 ms/step vs 228.2 ms fused, profiles/RESULTS.md):
+        # one 16 KB x 2 bounce ring per CTA does not keep enough NVLink bytes in flight to feed a GEMM that consumes
+        # 7/8 remote weights, while the copy engines prefetch a whole layer ahead for free.
         self.fused_gather = (self.use_kernels and self.is_llama and world_size > 1 and esize == 2 and init_fn is None
-                             and os.environ.get("DTG_FSDP_GATHER", "gemm") == "gemm")
+                             and os.environ.get("DTG_FSDP_GATHER", "ce") == "gemm")
 
         def pick_chunk(named):
             """largest power-of-two chunk (16 KB .. 512 KB) that tiles every matrix of the group; 0 = not eligible"""
@@ -241,6 +244,7 @@ class FSDPEngine:
             self.rs_done: Dict[str, torch.cuda.Event] = {}
             self._done = torch.cuda.Event()
         self._in_backward = False
+        self._tails = []
         self.optimizer: Optional[FlatAdamW] = None
         # DTG_COMM_TRACE=1: CUDA events around every gather / reduce kernel and around every point where the
         # compute stream waits for the communication stream (see comm_trace_summary)
@@ -505,6 +509,24 @@ class FSDPEngine:
         self._unsharded.discard("embed")
         if self.use_kernels:
             self._done.record(self.comm_stream)
+            if self.measure_tail:
+                # exposed communication: how long the communication stream runs past the end of backward
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                d = torch.cuda.Event(enable_timing=True)
+                d.record(self.comm_stream)
+                self._tails.append((e, d))
+
+    measure_tail = False
+
+    def exposed_comm_ms(self, last_steps=None):
+        """Mean time per step the communication stream (reduce-scatter + AdamW of the last groups) kept running after
+        backward had finished on the compute stream; None if not measured (bench.py sets ``measure_tail``)."""
+        tails = self._tails[-last_steps:] if last_steps else self._tails
+        if not tails:
+            return None
+        torch.cuda.synchronize()
+        return sum(max(0.0, a.elapsed_time(b)) for a, b in tails) / len(tails)
 
     @contextlib.contextmanager
     def no_sync(self):

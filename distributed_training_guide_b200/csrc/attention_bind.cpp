@@ -19,14 +19,14 @@ void check_qkv(const Tensor& qkv, int64_t nh, int64_t nkv) {
               "qkv must be [B, S, nh+2*nkv, 128]");
 }
 
-// version: 0 = default (DTG_ATTN_FWD env, else 1), 1 = one query tile per CTA (attention_fwd.cu),
+// version: 0 = default (DTG_ATTN_FWD env, else 2), 1 = one query tile per CTA (attention_fwd.cu),
 // 2 = two tiles per CTA, P kept in tensor memory (attention_fwd2.cu)
 int default_fwd_version() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("DTG_ATTN_FWD");
-    v = e ? atoi(e) : 1;
-    if (v != 1 && v != 2) v = 1;
+    v = e ? atoi(e) : 2;
+    if (v != 1 && v != 2) v = 2;
   }
   return v;
 }

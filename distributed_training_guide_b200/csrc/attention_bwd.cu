@@ -395,9 +395,9 @@ void attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse,
     DTG_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SMEM_BYTES));
     attr = true;
   }
-  static const bool ts_default = []() {   // DTG_ATTN_BWD=ts|ss
+  static const bool ts_default = []() {   // DTG_ATTN_BWD=ts (default: P / dS stay in tensor memory) | ss
     const char* e = getenv("DTG_ATTN_BWD");
-    return e ? e[0] == 't' : false;
+    return e ? e[0] == 't' : true;
   }();
   const bool ts = mode == 0 ? ts_default : mode == 2;   // mode: 0 default, 1 = ss, 2 = ts
   const int nblk = S / 128;

@@ -272,12 +272,15 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         float sum4[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t pk[64];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t r0[32], r1[32];
-          tmem_ld_32x32b_x32(s_addr + h * 64, r0);
-          tmem_ld_32x32b_x32(s_addr + h * 64 + 32, r1);
-          tmem_ld_wait();
+        // the whole 128-column row in flight behind ONE wait: the softmax phase is bound by tensor-memory round
+        // trips (few warps, each serialising its tcgen05.ld -> wait), not by instruction issue or the SFU
+        uint32_t ra[32], rb[32], rc[32], rd[32];
+        tmem_ld_32x32b_x32(s_addr, ra);
+        tmem_ld_32x32b_x32(s_addr + 32, rb);
+        tmem_ld_32x32b_x32(s_addr + 64, rc);
+        tmem_ld_32x32b_x32(s_addr + 96, rd);
+        tmem_ld_wait();
+        auto half = [&](const uint32_t(&r0)[32], const uint32_t(&r1)[32], int h) {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const float a0 = __uint_as_float(r0[i]), a1 = __uint_as_float(r0[i + 1]);
@@ -291,7 +294,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
             pk[h * 32 + (i >> 1)] = *reinterpret_cast<uint32_t*>(&lo);
             pk[h * 32 + 16 + (i >> 1)] = *reinterpret_cast<uint32_t*>(&hi);
           }
-        }
+        };
+        half(ra, rb, 0);
+        half(rc, rd, 1);
         const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         if (__any_sync(0xffffffffu, (mx - m_use) * scale_log2 > RESCALE_LOG2)) return false;
         uint32_t(&lo32)[32] = *reinterpret_cast<uint32_t(*)[32]>(&pk[0]);

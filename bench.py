@@ -191,6 +191,10 @@ def _stall_report(idle_s):
         symm = sys.modules.get("distributed_training_guide_b200.parallel.symm")
         for line in (symm.post_mortem(timeout_s=3.0) if symm is not None else []):
             w.write(f"[bench rank {rank}] {line}\n")
+        ms = torch.cuda.memory_stats(eng.device)
+        w.write(f"[bench rank {rank}] allocator: reserved {ms.get('reserved_bytes.all.peak', 0) / 1e9:.1f} GB peak, "
+                f"alloc retries {ms.get('num_alloc_retries', 0)} (a retry = cudaFree of cached blocks = device-wide "
+                f"synchronisation while peers spin)\n")
     except Exception as e:  # pragma: no cover - diagnostics only
         w.write(f"[bench rank {rank}] (device state unavailable: {e!r})\n")
     w.flush()
@@ -307,7 +311,9 @@ def run_b200(args):
     launches = _ext.launch_count() - l0
     ms_dev = _dist_max(s.elapsed_time(e), dev) / args.steps
     _stage(f"device-timed region: {ms_dev:.2f} ms/step = {1000.0 * eng.tokens_per_step / ms_dev:.0f} tokens/s "
-           f"(interim; the JSON line follows the end-to-end region)")
+           f"(interim; the JSON line follows the end-to-end region); reserved "
+           f"{torch.cuda.max_memory_reserved(dev) / 1e9:.1f} GB, alloc retries "
+           f"{int(torch.cuda.memory_stats(dev).get('num_alloc_retries', 0))}")
     # ---- region 2: end to end through the public API: pinned H2D every step + loss D2H every step ---
     _stage(f"timing {args.steps} steps end to end (pinned H2D + loss D2H every step)", budget_s=BUDGET["e2e"] + 2 * args.steps)
     eng.step(host_batches[args.steps])
@@ -348,6 +354,8 @@ def run_b200(args):
         **({"comm_trace": eng.model.engine.comm_trace_summary(last_steps=args.steps)}
            if getattr(getattr(eng.model, "engine", None), "trace", None) else {}),
         "peak_alloc_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
+        "peak_reserved_gb": torch.cuda.max_memory_reserved(dev) / 1e9,
+        "alloc_retries": int(torch.cuda.memory_stats(dev).get("num_alloc_retries", 0)),
     }
     if rank == 0:
         print(json.dumps(out), flush=True)

@@ -304,10 +304,12 @@ def run_b200(args):
     with ClockSampler(dev.index or 0) as clocks:
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
+        _tick()
         for i in range(args.steps):
             loss = eng.step(dev_batches[args.warmup + 1 + i])
         e.record()
         _barrier_sync(dev)
+    _PROGRESS["t"] = None
     launches = _ext.launch_count() - l0
     ms_dev = _dist_max(s.elapsed_time(e), dev) / args.steps
     _stage(f"device-timed region: {ms_dev:.2f} ms/step = {1000.0 * eng.tokens_per_step / ms_dev:.0f} tokens/s "
@@ -318,6 +320,7 @@ def run_b200(args):
     _stage(f"timing {args.steps} steps end to end (pinned H2D + loss D2H every step)", budget_s=BUDGET["e2e"] + 2 * args.steps)
     eng.step(host_batches[args.steps])
     _barrier_sync(dev)
+    _tick()
     s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     s2.record()
@@ -325,7 +328,9 @@ def run_b200(args):
     for i in range(args.steps):
         loss = eng.step(host_batches[i])
         last = loss.item()  # 4-byte device->host read of the step's result
+        _tick()             # (stall reporter: this loop synchronises every step, so a missing tick is a real stall)
     e2.record()
+    _PROGRESS["t"] = None
     _barrier_sync(dev)
     wall_ms = 1000 * (time.perf_counter() - t0)
     ms_e2e = _dist_max(max(s2.elapsed_time(e2), wall_ms), dev) / args.steps

@@ -32,7 +32,8 @@ KERNELS = [
     ("rope_inplace", r"rope_inplace_kernel", ""),
     ("swiglu_fwd", r"swiglu_fwd_kernel", ""),
     ("swiglu_bwd", r"swiglu_bwd_kernel", ""),
-    ("cross_entropy", r"cross_entropy_fwd_bwd_kernel|ce_fwd_bwd", "in-place dlogits"),
+    ("cross_entropy", r"ce_row_kernel", "one CTA per row: online max/sum, dlogits written in place over the logits"),
+    ("embedding_fwd", r"embedding_fwd_kernel", ""),
     ("adamw_flat", r"adamw_flat_kernel", ""),
     ("embedding_bwd_sorted", r"embedding_bwd_sorted_kernel", "deterministic, no atomics"),
     ("zero1_bucket_nr8", r"rs_adamw_kernel<8, __nv_bfloat16, true>", "peer LD (pull) + AdamW + peer ST (push), device barrier"),

@@ -261,7 +261,12 @@ class FSDPEngine:
     def _install_gather_specs(self, model):
         """Give every matrix that a linear op reads (fused q|k|v and gate|up, o_proj, down_proj, lm_head) a
         ``_dtg_gather`` handle: ``ops._Linear`` then runs the GEMM that also gathers the weight from the ranks'
-        shards (first use after the group became live) or the plain GEMM (already gathered)."""
+        shards (first use after the group became live) or the plain GEMM (already gathered).
+
+        Reference: FSDP2's per-layer all-gather in front of the layer's first matmul and again in backward
+        (``fully_shard(layer, reshard_after_forward=True)``, ``04-fully-sharded-data-parallel/train_llm.py:83-90``) and
+        the root ``model.unshard()`` prefetch (``04:187-188``): there three NCCL-side kernels per gather (copy-in,
+        all_gather_into_tensor, copy-out), here none — the bytes move inside the consuming tcgen05 GEMM."""
         self.gather_pads = self.symm.new_pad_set()   # these kernels run on the compute stream: own pad + epochs
         self._counters, self._ngather = {}, {}
         esize = 2

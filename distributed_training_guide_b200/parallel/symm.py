@@ -128,7 +128,8 @@ class _IpcChunk:
 
 
 class _VmmChunk:
-    """One VMM chunk (``csrc/symm_vmm.cpp``): my physical allocation + every peer's, mapped side by side, and the
+    """(The reference never owns communication memory — NCCL registers whatever torch passes it)
+    One VMM chunk (``csrc/symm_vmm.cpp``): my physical allocation + every peer's, mapped side by side, and the
     NVLS multicast view.  File descriptors travel over an abstract Unix socket (SCM_RIGHTS); ordering over the store."""
 
     def __init__(self, group, nbytes):

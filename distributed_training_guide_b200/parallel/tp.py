@@ -98,7 +98,10 @@ class TPContext:
                             self.symm._epochs(1), self.n_comm)
 
     def row_parallel_gemm(self, a, w, trans_b, residual):
-        """reduce_scatter_rows(a @ op(w)) (+ residual) -> [T/t, H] for this rank (GPU kernels)."""
+        """reduce_scatter_rows(a @ op(w)) (+ residual) -> [T/t, H] for this rank (GPU kernels).
+
+        Reference: ``RowwiseParallel(output_layouts=Shard(1))`` on ``o_proj`` / ``down_proj``
+        (``06-tensor-parallel/train_llm.py:99,108``): a cuBLAS GEMM followed by a standalone NCCL reduce-scatter."""
         C = self.symm.C
         T, Tl, H = a.shape[0], self.rpp, self.H
         y = torch.empty(Tl, H, dtype=a.dtype, device=a.device)

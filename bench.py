@@ -310,6 +310,7 @@ def run_b200(args):
         e.record()
         _barrier_sync(dev)
     _PROGRESS["t"] = None
+    eng.strategy.check_health()   # a device-side barrier that timed out inside the timed region invalidates it: fail loudly
     launches = _ext.launch_count() - l0
     ms_dev = _dist_max(s.elapsed_time(e), dev) / args.steps
     _stage(f"device-timed region: {ms_dev:.2f} ms/step = {1000.0 * eng.tokens_per_step / ms_dev:.0f} tokens/s "
@@ -333,6 +334,7 @@ def run_b200(args):
     _PROGRESS["t"] = None
     _barrier_sync(dev)
     wall_ms = 1000 * (time.perf_counter() - t0)
+    eng.strategy.check_health()
     ms_e2e = _dist_max(max(s2.elapsed_time(e2), wall_ms), dev) / args.steps
 
     tokens = eng.tokens_per_step
